@@ -1,0 +1,158 @@
+/*
+ * joeys2t_b200 — C ABI of the B200-native audio front-end (fbank -> CMVN -> SpecAugment).
+ *
+ * This is the drop-in boundary for JoeyS2T's front-end hot path.  The reference is pure Python; the
+ * functions it would bind through ctypes/cffi are listed below with the reference interface each
+ * one replaces (paths relative to the reference repository root; "TA:" = the un-vendored PyPI
+ * dependency torchaudio/compliance/kaldi.py that holds the arithmetic).  INTEGRATION.md shows the
+ * ctypes stub a maintainer would add to joeynmt/helpers_for_audio.py / data_augmentation.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types;
+ *   - every function returns an int status (JS2T_OK == 0); js2t_last_error() gives the text of the
+ *     last failure on the calling thread; no exceptions cross the boundary;
+ *   - pointers named *_dev are CUDA device pointers owned by the caller, everything else is host
+ *     memory; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - all GPU work is enqueued asynchronously on `stream`; nothing here synchronises the device
+ *     except js2t_plan_create / js2t_ctx_create / *_destroy (allocation);
+ *   - there is no CPU fallback: without a usable CUDA device every call fails with JS2T_ERR_CUDA.
+ *
+ * Geometry is the reference's fixed one: 16 kHz, 25 ms / 10 ms frames (400 / 160 samples),
+ * 512-point FFT, 80 mel bins, dither 0 (joeynmt/helpers_for_audio.py:34-36 passes only
+ * num_mel_bins and sample_frequency; TA:514-541 defaults).
+ */
+#ifndef JOEYS2T_B200_H_
+#define JOEYS2T_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JS2T_VERSION 100 /* 0.1.0 */
+
+enum {
+  JS2T_OK = 0,
+  JS2T_ERR_INVALID = 1,     /* bad argument */
+  JS2T_ERR_CUDA = 2,        /* CUDA runtime error (text in js2t_last_error) */
+  JS2T_ERR_SHORT_INPUT = 3, /* an utterance is shorter than one 400-sample window (TA:142-144) */
+  JS2T_ERR_TABLES = 4,      /* uploaded mel bank does not match the compiled-in structure */
+  JS2T_ERR_NCCL = 5,        /* NCCL unavailable or failed */
+  JS2T_ERR_STATE = 6        /* call sequence error (e.g. normalise before statistics exist) */
+};
+
+/* CMVN modes of a plan */
+enum {
+  JS2T_CMVN_NONE = 0,      /* raw log-mel (extract_fbank_features only) */
+  JS2T_CMVN_UTTERANCE = 1, /* joeynmt/data_augmentation.py:83-115 CMVN, per utterance */
+  JS2T_CMVN_GLOBAL = 2,    /* corpus-level statistics supplied with js2t_plan_set_global_stats
+                              or js2t_global_stats_finalize (extension) */
+  JS2T_CMVN_STATS_ONLY = 3 /* raw log-mel + per-utterance fp64 sum / sum-of-squares */
+};
+
+/* output layouts */
+enum {
+  JS2T_LAYOUT_RAGGED = 0, /* (sum_u T_u, 80): utterances back to back */
+  JS2T_LAYOUT_PADDED = 1  /* (B, Tmax, 80) filled with pad_value, joeynmt/helpers_for_audio.py:130-170 */
+};
+
+enum { JS2T_MASK_VALUE_MEAN = 0, JS2T_MASK_VALUE_CONST = 1 };
+
+typedef struct js2t_ctx js2t_ctx;   /* per device: tables */
+typedef struct js2t_plan js2t_plan; /* per batch geometry: descriptors + workspace */
+
+int js2t_version(void);
+const char* js2t_last_error(void);
+
+/* Frame count for n_samples at 16 kHz with snip_edges=True: 1 + (n - 400) / 160, 0 if n < 400.
+ * Replaces the shape logic of TA:44-83 (_get_strided); cf. joeynmt/helpers_for_audio.py:93-96. */
+int64_t js2t_num_frames(int64_t n_samples);
+
+/* ---- context ------------------------------------------------------------------------------- */
+int js2t_ctx_create(int device, js2t_ctx** out);
+int js2t_ctx_destroy(js2t_ctx* ctx);
+
+/* Upload the povey window (400 floats, TA:98-100) and the dense mel bank (80 x 256 floats,
+ * row-major, TA:436-511).  The bank must have the two-adjacent-filters-per-bin structure of the
+ * reference configuration, otherwise JS2T_ERR_TABLES.  Must be called once before any execute. */
+int js2t_ctx_set_tables(js2t_ctx* ctx, const float* window400, const float* mel80x256);
+
+/* ---- plan: one ragged batch ------------------------------------------------------------------
+ * n_utts utterances packed in one PCM buffer.  pcm_byte_off[u] (multiple of 16) is where utterance
+ * u starts, n_samples[u] its length, is_f32[u] != 0 means float32 samples in [-1, 1) (the loader's
+ * output, scaled by 2^15 on the fly: joeynmt/helpers_for_audio.py:54), else int16 PCM.
+ * max_frames[u] > 0 truncates to the first max_frames[u] frames *before* CMVN
+ * (joeynmt/tokenizers.py:477-484, evaluation branch); pass NULL for no truncation.
+ * Fails with JS2T_ERR_SHORT_INPUT if any utterance has fewer than 400 samples. */
+int js2t_plan_create(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte_off,
+                     const int64_t* n_samples, const uint8_t* is_f32, const int32_t* max_frames,
+                     int layout, int pad_tmax, float pad_value, js2t_plan** out);
+/* Same, for pre-extracted features (the .npy / npy-in-zip branch of get_features,
+ * joeynmt/helpers_for_audio.py:100-127): the input of js2t_features_execute is (sum_u n_frames[u], 80)
+ * float32, utterances back to back.  Lets CMVN / SpecAugment / pad_features run on their own. */
+int js2t_plan_create_features(js2t_ctx* ctx, int n_utts, const int32_t* n_frames,
+                              const int32_t* max_frames, int layout, int pad_tmax, float pad_value,
+                              js2t_plan** out);
+int js2t_plan_destroy(js2t_plan* plan);
+
+int64_t js2t_plan_total_frames(const js2t_plan* plan); /* sum of emitted frames */
+int64_t js2t_plan_out_rows(const js2t_plan* plan);     /* rows of 80 floats the output needs */
+int js2t_plan_get_frames(const js2t_plan* plan, int32_t* n_frames_out);   /* [n_utts] */
+int js2t_plan_get_out_rows(const js2t_plan* plan, int64_t* first_row_out); /* [n_utts] */
+
+/* CMVN(norm_means, norm_vars, before): joeynmt/data_augmentation.py:89-109 and the call order of
+ * joeynmt/tokenizers.py:488-493 (before != 0: CMVN then SpecAugment; else SpecAugment then CMVN). */
+int js2t_plan_set_cmvn(js2t_plan* plan, int mode, int norm_means, int norm_vars, int before);
+
+/* Global CMVN statistics known up front: per-bin mean and 1/std (80 doubles each, host). */
+int js2t_plan_set_global_stats(js2t_plan* plan, const double* mean80, const double* istd80,
+                               void* stream);
+
+/* SpecAugment fill (joeynmt/data_augmentation.py:54-70) for masks drawn on the host:
+ * table is int32 [n_utts][n_fmask + n_tmask][2] = (start, width), frequency masks first; width 0
+ * is a no-op (the reference still consumes the RNG draws for it).  value_mode MEAN reproduces
+ * `mask_value = spectrogram.mean()` (:45-46), CONST uses value_const.  table == NULL clears. */
+int js2t_plan_set_masks(js2t_plan* plan, int n_fmask, int n_tmask, const int32_t* table,
+                        int value_mode, float value_const, void* stream);
+
+/* ---- the hot path ---------------------------------------------------------------------------
+ * pcm_dev -> out_dev according to the plan (fbank [-> CMVN] [-> SpecAugment], padded or ragged).
+ * Replaces the per-utterance chain
+ *   joeynmt/helpers_for_audio.py:41-68 extract_fbank_features -> TA:514-645 fbank
+ *   joeynmt/data_augmentation.py:96-109 CMVN.__call__, :38-73 SpecAugment.__call__
+ *   joeynmt/helpers_for_audio.py:130-170 pad_features
+ * for a whole batch.  out_dev must hold js2t_plan_out_rows() * 80 floats. */
+int js2t_fbank_execute(js2t_plan* plan, const void* pcm_dev, float* out_dev, void* stream);
+
+/* feats_dev -> out_dev: [CMVN] [SpecAugment] [padding] on pre-extracted features
+ * (joeynmt/data_augmentation.py:96-109, :38-73; joeynmt/helpers_for_audio.py:130-170).
+ * feats_dev == out_dev (ragged layout) is allowed. */
+int js2t_features_execute(js2t_plan* plan, const float* feats_dev, float* out_dev, void* stream);
+
+/* Instrumentation for bench.py: bracket the dominant (fbank) kernel of every execute with CUDA
+ * events on the launching stream (ring of n_slots; 0 disables) and read the durations back. */
+int js2t_plan_enable_profiling(js2t_plan* plan, int n_slots);
+int js2t_plan_kernel_times_ms(js2t_plan* plan, float* ms_out, int n, int* n_written);
+
+/* Device pointer to the per-utterance fp64 statistics [n_utts][160] (sum | sum of squares of the
+ * raw log-mel) produced by the last execute in UTTERANCE / STATS_ONLY / masked modes. */
+int js2t_plan_utt_stats(const js2t_plan* plan, const double** stats_dev);
+
+/* ---- global CMVN (multi-GPU) ----------------------------------------------------------------
+ * accum_dev: 161 doubles on the device = per-bin sum[80] | sumsq[80] | frame count.
+ * accumulate adds this plan's statistics (fixed summation order, deterministic);
+ * allreduce sums accum_dev over all ranks with one ncclAllReduce (comm is a ncclComm_t);
+ * finalize turns accum_dev into the plan's mean / inverse std with the reference formula
+ * (var = sumsq/n - mean^2, std = sqrt(max(var, 1e-10)), joeynmt/data_augmentation.py:98-105);
+ * normalize applies them (and the SpecAugment fill) in place to raw log-mel in out_dev. */
+int js2t_global_stats_accumulate(js2t_plan* plan, double* accum_dev, void* stream);
+int js2t_global_stats_allreduce(void* nccl_comm, double* accum_dev, void* stream);
+int js2t_global_stats_finalize(js2t_plan* plan, const double* accum_dev, void* stream);
+int js2t_normalize_execute(js2t_plan* plan, float* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JOEYS2T_B200_H_ */

@@ -1,0 +1,136 @@
+# coding: utf-8
+"""
+ctypes binding of ``libjoeys2t_b200.so`` (the C ABI declared in ``include/joeys2t_b200.h``).
+
+The shared library is built in-tree (``joeys2t_b200/csrc/libjoeys2t_b200.so``) by
+:func:`build` / ``__graft_entry__.build()`` with ``nvcc -gencode arch=compute_100a,code=sm_100a``.
+There is **no CPU fallback**: if the library is missing or no CUDA device is usable, every entry
+point raises.
+"""
+import ctypes
+import os
+import subprocess
+import threading
+from pathlib import Path
+
+CSRC = Path(__file__).resolve().parent / "csrc"
+LIB_PATH = CSRC / "libjoeys2t_b200.so"
+SOURCES = ["fbank_kernels.cu", "capi.cu"]
+HEADERS = ["js2t_internal.h", "mel_structure.inc", "../../include/joeys2t_b200.h"]
+
+# status codes (include/joeys2t_b200.h)
+OK, ERR_INVALID, ERR_CUDA, ERR_SHORT_INPUT, ERR_TABLES, ERR_NCCL, ERR_STATE = range(7)
+CMVN_NONE, CMVN_UTTERANCE, CMVN_GLOBAL, CMVN_STATS_ONLY = range(4)
+LAYOUT_RAGGED, LAYOUT_PADDED = 0, 1
+MASK_VALUE_MEAN, MASK_VALUE_CONST = 0, 1
+
+# every symbol include/joeys2t_b200.h declares (tests check the .so exports all of them)
+EXPORTED_SYMBOLS = [
+    "js2t_version", "js2t_last_error", "js2t_num_frames", "js2t_ctx_create", "js2t_ctx_destroy",
+    "js2t_ctx_set_tables", "js2t_plan_create", "js2t_plan_create_features", "js2t_plan_destroy",
+    "js2t_plan_total_frames", "js2t_plan_out_rows", "js2t_plan_get_frames", "js2t_plan_get_out_rows",
+    "js2t_plan_set_cmvn", "js2t_plan_set_global_stats", "js2t_plan_set_masks", "js2t_fbank_execute",
+    "js2t_features_execute", "js2t_plan_enable_profiling", "js2t_plan_kernel_times_ms",
+    "js2t_plan_utt_stats", "js2t_global_stats_accumulate",
+    "js2t_global_stats_allreduce", "js2t_global_stats_finalize", "js2t_normalize_execute",
+]
+
+
+class Js2tError(RuntimeError):
+    """A C-ABI call returned a non-zero status."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[js2t status {code}] {message}")
+        self.code = code
+
+
+def nvcc_command(out: Path = LIB_PATH, extra=()):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    return [
+        nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+        "--shared", "-Xcompiler", "-fPIC", *extra, "-o", str(out), *[str(CSRC / s) for s in SOURCES],
+        "-ldl"
+    ]
+
+
+def is_stale() -> bool:
+    if not LIB_PATH.is_file():
+        return True
+    t = LIB_PATH.stat().st_mtime
+    return any((CSRC / f).resolve().stat().st_mtime > t for f in SOURCES + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile the CUDA library for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    if not force and not is_stale():
+        return LIB_PATH
+    cmd = nvcc_command(extra=("-Xptxas", "-v") if verbose else ())
+    res = subprocess.run(cmd, capture_output=True, text=True, cwd=str(CSRC))
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed ({' '.join(cmd)}):\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def _declare(lib):
+    c = ctypes
+    vp, i32, i64, f32 = c.c_void_p, c.c_int, c.c_int64, c.c_float
+    P = c.POINTER
+    lib.js2t_version.restype = i32
+    lib.js2t_last_error.restype = c.c_char_p
+    lib.js2t_num_frames.restype = i64
+    lib.js2t_num_frames.argtypes = [i64]
+    lib.js2t_ctx_create.argtypes = [i32, P(vp)]
+    lib.js2t_ctx_destroy.argtypes = [vp]
+    lib.js2t_ctx_set_tables.argtypes = [vp, vp, vp]
+    lib.js2t_plan_create.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, f32, P(vp)]
+    lib.js2t_plan_create_features.argtypes = [vp, i32, vp, vp, i32, i32, f32, P(vp)]
+    lib.js2t_plan_destroy.argtypes = [vp]
+    lib.js2t_plan_total_frames.restype = i64
+    lib.js2t_plan_total_frames.argtypes = [vp]
+    lib.js2t_plan_out_rows.restype = i64
+    lib.js2t_plan_out_rows.argtypes = [vp]
+    lib.js2t_plan_get_frames.argtypes = [vp, vp]
+    lib.js2t_plan_get_out_rows.argtypes = [vp, vp]
+    lib.js2t_plan_set_cmvn.argtypes = [vp, i32, i32, i32, i32]
+    lib.js2t_plan_set_global_stats.argtypes = [vp, vp, vp, vp]
+    lib.js2t_plan_set_masks.argtypes = [vp, i32, i32, vp, i32, f32, vp]
+    lib.js2t_fbank_execute.argtypes = [vp, vp, vp, vp]
+    lib.js2t_features_execute.argtypes = [vp, vp, vp, vp]
+    lib.js2t_plan_enable_profiling.argtypes = [vp, i32]
+    lib.js2t_plan_kernel_times_ms.argtypes = [vp, vp, i32, P(i32)]
+    lib.js2t_plan_utt_stats.argtypes = [vp, P(vp)]
+    lib.js2t_global_stats_accumulate.argtypes = [vp, vp, vp]
+    lib.js2t_global_stats_allreduce.argtypes = [vp, vp, vp]
+    lib.js2t_global_stats_finalize.argtypes = [vp, vp, vp]
+    lib.js2t_normalize_execute.argtypes = [vp, vp, vp]
+    for name in EXPORTED_SYMBOLS:
+        fn = getattr(lib, name)
+        if fn.restype is c.c_int and name not in ("js2t_version",):
+            fn.restype = i32
+
+
+def load():
+    """Load (once) and return the ctypes handle.  Raises if the library has not been built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not LIB_PATH.is_file():
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: the CUDA extension has not been built. Run "
+                    "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
+                    "There is no CPU fallback.")
+            lib = ctypes.CDLL(str(LIB_PATH))
+            _declare(lib)
+            _lib = lib
+    return _lib
+
+
+def check(status: int):
+    if status != OK:
+        raise Js2tError(status, load().js2t_last_error().decode("utf-8", "replace"))

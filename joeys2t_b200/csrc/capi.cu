@@ -1,0 +1,617 @@
+// extern "C" surface of libjoeys2t_b200.so — see include/joeys2t_b200.h for the contract and the
+// reference interfaces each entry point replaces.
+#include "../../include/joeys2t_b200.h"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "js2t_internal.h"
+#include "mel_structure.inc"
+
+using namespace js2t;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define JS2T_CUDA(expr)                                                                    \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return fail(JS2T_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                  __FILE__, __LINE__);                                                     \
+  } while (0)
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+struct js2t_ctx {
+  int device = 0;
+  float* d_tables = nullptr;  // window_half[400] | tw256[256 x float2] | tw512[136 x float2]
+  bool tables_set = false;
+};
+
+struct js2t_plan {
+  js2t_ctx* ctx = nullptr;
+  int n_utts = 0, n_tiles = 0;
+  int layout = JS2T_LAYOUT_RAGGED, pad_tmax = 0;
+  float pad_value = 1.0f;
+  long long total_frames = 0, out_rows = 0;
+  std::vector<UttDesc> h_utts;
+  // device workspace (one allocation)
+  void* d_ws = nullptr;
+  UttDesc* d_utts = nullptr;
+  TileDesc* d_tiles = nullptr;
+  float* d_tile_stats = nullptr;
+  float* d_mean = nullptr;
+  float* d_istd = nullptr;
+  float* d_mask_value = nullptr;
+  float* d_gmean = nullptr;
+  float* d_gistd = nullptr;
+  double* d_utt_stats = nullptr;
+  int* d_masks = nullptr;
+  size_t masks_cap = 0;
+  // configuration
+  int cmvn_mode = JS2T_CMVN_NONE, norm_means = 1, norm_vars = 1, before = 1;
+  int n_fmask = 0, n_tmask = 0, mask_value_mode = JS2T_MASK_VALUE_MEAN;
+  float mask_value_const = 0.f;
+  bool has_masks = false, global_stats_set = false, stats_valid = false;
+  bool feature_input = false;  // rows of 80 floats instead of PCM (js2t_plan_create_features)
+  // optional instrumentation: CUDA events around the fbank kernel of each execute (ring of slots)
+  std::vector<cudaEvent_t> prof_ev;  // 2 per slot
+  long long prof_calls = 0;
+};
+
+extern "C" {
+
+int js2t_version(void) { return JS2T_VERSION; }
+const char* js2t_last_error(void) { return g_err; }
+
+int64_t js2t_num_frames(int64_t n_samples) {
+  return n_samples < kFrameLen ? 0 : 1 + (n_samples - kFrameLen) / kHop;
+}
+
+// ---------------------------------------------------------------------------------------------
+int js2t_ctx_create(int device, js2t_ctx** out) {
+  if (out == nullptr) return fail(JS2T_ERR_INVALID, "js2t_ctx_create: out is NULL");
+  int n_dev = 0;
+  JS2T_CUDA(cudaGetDeviceCount(&n_dev));
+  if (device < 0 || device >= n_dev)
+    return fail(JS2T_ERR_CUDA, "js2t_ctx_create: device %d not available (%d CUDA devices)", device, n_dev);
+  cudaDeviceProp prop;
+  JS2T_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(JS2T_ERR_CUDA, "js2t_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                device, prop.major, prop.minor);
+  JS2T_CUDA(cudaSetDevice(device));
+  js2t_ctx* c = new (std::nothrow) js2t_ctx();
+  if (c == nullptr) return fail(JS2T_ERR_INVALID, "out of host memory");
+  c->device = device;
+  const size_t bytes = (400 + 2 * 256 + 2 * 136) * sizeof(float);
+  cudaError_t e = cudaMalloc(&c->d_tables, bytes);
+  if (e != cudaSuccess) {
+    delete c;
+    return fail(JS2T_ERR_CUDA, "cudaMalloc(tables) failed: %s", cudaGetErrorString(e));
+  }
+  *out = c;
+  return JS2T_OK;
+}
+
+int js2t_ctx_destroy(js2t_ctx* ctx) {
+  if (ctx == nullptr) return JS2T_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->d_tables) cudaFree(ctx->d_tables);
+  delete ctx;
+  return JS2T_OK;
+}
+
+int js2t_ctx_set_tables(js2t_ctx* ctx, const float* window400, const float* mel80x256) {
+  if (ctx == nullptr || window400 == nullptr || mel80x256 == nullptr)
+    return fail(JS2T_ERR_INVALID, "js2t_ctx_set_tables: NULL argument");
+  // ---- mel bank -> two-band form, validated against the compiled-in structure ----------------
+  float wu[256], wd[256];
+  memset(wu, 0, sizeof(wu));
+  memset(wd, 0, sizeof(wd));
+  std::vector<float> dense(80 * 256, 0.f);
+  for (int s = 0; s < JS2T_MEL_NUM_SEGMENTS; ++s) {
+    for (int k = kMelSegLo[s]; k <= kMelSegHi[s]; ++k) {
+      if (s < 80) { wu[k] = mel80x256[s * 256 + k]; dense[s * 256 + k] = wu[k]; }
+      if (s >= 1) { wd[k] = mel80x256[(s - 1) * 256 + k]; dense[(s - 1) * 256 + k] = wd[k]; }
+    }
+  }
+  for (int i = 0; i < 80 * 256; ++i) {
+    if (dense[i] != mel80x256[i])
+      return fail(JS2T_ERR_TABLES,
+                  "mel bank entry (filter %d, bin %d) = %g is outside the compiled-in two-band structure "
+                  "(16 kHz, 512-point FFT, 80 bins, 20 Hz..Nyquist)", i / 256, i % 256, (double)mel80x256[i]);
+  }
+  // ---- window (x 0.5: folds the 1/2 of the real-FFT split; exact power-of-two scaling) --------
+  std::vector<float> host(400 + 2 * 256 + 2 * 136);
+  if (window400[0] != 0.f)
+    return fail(JS2T_ERR_TABLES, "window[0] must be 0 (povey); the staging of x[j-1] relies on it");
+  for (int i = 0; i < 400; ++i) host[i] = 0.5f * window400[i];
+  const double two_pi = 6.283185307179586476925286766559;
+  float* tw256 = host.data() + 400;
+  for (int k1 = 0; k1 < 16; ++k1)
+    for (int n2 = 0; n2 < 16; ++n2) {
+      const double a = -two_pi * (double)(n2 * k1) / 256.0;
+      tw256[2 * (k1 * 16 + n2)] = (float)cos(a);
+      tw256[2 * (k1 * 16 + n2) + 1] = (float)sin(a);
+    }
+  float* tw512 = tw256 + 2 * 256;
+  for (int k = 0; k < 136; ++k) {
+    const double a = -two_pi * (double)k / 512.0;
+    tw512[2 * k] = (float)cos(a);
+    tw512[2 * k + 1] = (float)sin(a);
+  }
+  JS2T_CUDA(cudaSetDevice(ctx->device));
+  JS2T_CUDA(cudaMemcpy(ctx->d_tables, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+  JS2T_CUDA(upload_mel_weights(wu, wd, 0));
+  JS2T_CUDA(cudaStreamSynchronize(0));
+  ctx->tables_set = true;
+  return JS2T_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// n_frames_in != NULL: feature-input plan (rows of 80 floats, packed back to back)
+static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte_off, const int64_t* n_samples,
+                              const uint8_t* is_f32, const int32_t* max_frames, const int32_t* n_frames_in,
+                              int layout, int pad_tmax, float pad_value, js2t_plan** out) {
+  const bool feat = n_frames_in != nullptr;
+  if (ctx == nullptr || out == nullptr || (!feat && (pcm_byte_off == nullptr || n_samples == nullptr)))
+    return fail(JS2T_ERR_INVALID, "js2t_plan_create: NULL argument");
+  if (n_utts <= 0) return fail(JS2T_ERR_INVALID, "js2t_plan_create: n_utts = %d", n_utts);
+  if (layout != JS2T_LAYOUT_RAGGED && layout != JS2T_LAYOUT_PADDED)
+    return fail(JS2T_ERR_INVALID, "js2t_plan_create: unknown layout %d", layout);
+  js2t_plan* p = new (std::nothrow) js2t_plan();
+  if (p == nullptr) return fail(JS2T_ERR_INVALID, "out of host memory");
+  p->ctx = ctx;
+  p->n_utts = n_utts;
+  p->layout = layout;
+  p->pad_value = pad_value;
+  p->h_utts.resize(n_utts);
+  long long tmax = 0;
+  p->feature_input = feat;
+  long long in_row = 0;
+  for (int u = 0; feat && u < n_utts; ++u) {
+    long long T = n_frames_in[u];
+    if (T <= 0) {
+      delete p;
+      return fail(JS2T_ERR_INVALID, "utterance %d: empty feature! (%lld frames)", u, T);
+    }
+    UttDesc& d = p->h_utts[u];
+    d.pcm_byte_off = in_row * (long long)(kMel * sizeof(float));
+    in_row += T;
+    if (max_frames != nullptr && max_frames[u] > 0 && T > max_frames[u]) T = max_frames[u];
+    d.n_samples = 0;
+    d.n_frames = (int)T;
+    d.flags = 2;
+    p->total_frames += T;
+    if (T > tmax) tmax = T;
+  }
+  for (int u = 0; !feat && u < n_utts; ++u) {
+    if (pcm_byte_off[u] % 16 != 0) {
+      delete p;
+      return fail(JS2T_ERR_INVALID, "utterance %d: pcm_byte_off %lld is not 16-byte aligned", u,
+                  (long long)pcm_byte_off[u]);
+    }
+    long long T = js2t_num_frames(n_samples[u]);
+    if (T <= 0) {
+      delete p;
+      return fail(JS2T_ERR_SHORT_INPUT, "utterance %d: choose a window size 400 that is [2, %lld]", u,
+                  (long long)n_samples[u]);
+    }
+    if (n_samples[u] > 0x7fffffffLL) {
+      delete p;
+      return fail(JS2T_ERR_INVALID, "utterance %d: %lld samples exceed the 2^31-1 limit", u,
+                  (long long)n_samples[u]);
+    }
+    if (max_frames != nullptr && max_frames[u] > 0 && T > max_frames[u]) T = max_frames[u];
+    UttDesc& d = p->h_utts[u];
+    d.pcm_byte_off = pcm_byte_off[u];
+    d.n_samples = (int)n_samples[u];
+    d.n_frames = (int)T;
+    d.flags = (is_f32 != nullptr && is_f32[u]) ? 1 : 0;
+    p->total_frames += T;
+    if (T > tmax) tmax = T;
+  }
+  if (layout == JS2T_LAYOUT_PADDED) {
+    if (pad_tmax <= 0) pad_tmax = (int)tmax;
+    if (pad_tmax < tmax) {
+      delete p;
+      return fail(JS2T_ERR_INVALID, "padded layout: pad_tmax %d < longest utterance %lld frames", pad_tmax, tmax);
+    }
+    p->pad_tmax = pad_tmax;
+  }
+  std::vector<TileDesc> tiles;
+  long long row = 0;
+  for (int u = 0; u < n_utts; ++u) {
+    UttDesc& d = p->h_utts[u];
+    d.tile_start = (int)tiles.size();
+    const int span = layout == JS2T_LAYOUT_PADDED ? p->pad_tmax : d.n_frames;
+    d.out_row = row;
+    row += span;
+    for (int f0 = 0; f0 < span; f0 += kTileFrames) tiles.push_back(TileDesc{u, f0});
+  }
+  p->out_rows = row;
+  p->n_tiles = (int)tiles.size();
+
+  // one device allocation, carved up
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t o_utts = carve(sizeof(UttDesc) * n_utts);
+  const size_t o_tiles = carve(sizeof(TileDesc) * tiles.size());
+  const size_t o_tstats = carve(sizeof(float) * kStatsPerTile * tiles.size());
+  const size_t o_mean = carve(sizeof(float) * kMel * n_utts);
+  const size_t o_istd = carve(sizeof(float) * kMel * n_utts);
+  const size_t o_mv = carve(sizeof(float) * n_utts);
+  const size_t o_g = carve(sizeof(float) * 2 * kMel);
+  const size_t o_ustats = carve(sizeof(double) * kStatsPerTile * n_utts);
+  cudaSetDevice(ctx->device);
+  cudaError_t e = cudaMalloc(&p->d_ws, off);
+  if (e != cudaSuccess) {
+    delete p;
+    return fail(JS2T_ERR_CUDA, "cudaMalloc(%zu bytes of plan workspace) failed: %s", off, cudaGetErrorString(e));
+  }
+  char* base = static_cast<char*>(p->d_ws);
+  p->d_utts = reinterpret_cast<UttDesc*>(base + o_utts);
+  p->d_tiles = reinterpret_cast<TileDesc*>(base + o_tiles);
+  p->d_tile_stats = reinterpret_cast<float*>(base + o_tstats);
+  p->d_mean = reinterpret_cast<float*>(base + o_mean);
+  p->d_istd = reinterpret_cast<float*>(base + o_istd);
+  p->d_mask_value = reinterpret_cast<float*>(base + o_mv);
+  p->d_gmean = reinterpret_cast<float*>(base + o_g);
+  p->d_gistd = p->d_gmean + kMel;
+  p->d_utt_stats = reinterpret_cast<double*>(base + o_ustats);
+  e = cudaMemcpy(p->d_utts, p->h_utts.data(), sizeof(UttDesc) * n_utts, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(p->d_tiles, tiles.data(), sizeof(TileDesc) * tiles.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(p->d_ws);
+    delete p;
+    return fail(JS2T_ERR_CUDA, "plan descriptor upload failed: %s", cudaGetErrorString(e));
+  }
+  *out = p;
+  return JS2T_OK;
+}
+
+int js2t_plan_create(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte_off, const int64_t* n_samples,
+                     const uint8_t* is_f32, const int32_t* max_frames, int layout, int pad_tmax,
+                     float pad_value, js2t_plan** out) {
+  return plan_create_common(ctx, n_utts, pcm_byte_off, n_samples, is_f32, max_frames, nullptr, layout, pad_tmax,
+                            pad_value, out);
+}
+
+int js2t_plan_create_features(js2t_ctx* ctx, int n_utts, const int32_t* n_frames, const int32_t* max_frames,
+                              int layout, int pad_tmax, float pad_value, js2t_plan** out) {
+  if (n_frames == nullptr) return fail(JS2T_ERR_INVALID, "js2t_plan_create_features: n_frames is NULL");
+  return plan_create_common(ctx, n_utts, nullptr, nullptr, nullptr, max_frames, n_frames, layout, pad_tmax,
+                            pad_value, out);
+}
+
+int js2t_plan_destroy(js2t_plan* plan) {
+  if (plan == nullptr) return JS2T_OK;
+  cudaSetDevice(plan->ctx->device);
+  for (cudaEvent_t e : plan->prof_ev) cudaEventDestroy(e);
+  if (plan->d_masks) cudaFree(plan->d_masks);
+  if (plan->d_ws) cudaFree(plan->d_ws);
+  delete plan;
+  return JS2T_OK;
+}
+
+int64_t js2t_plan_total_frames(const js2t_plan* plan) { return plan ? plan->total_frames : -1; }
+int64_t js2t_plan_out_rows(const js2t_plan* plan) { return plan ? plan->out_rows : -1; }
+
+int js2t_plan_get_frames(const js2t_plan* plan, int32_t* n_frames_out) {
+  if (plan == nullptr || n_frames_out == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
+  for (int u = 0; u < plan->n_utts; ++u) n_frames_out[u] = plan->h_utts[u].n_frames;
+  return JS2T_OK;
+}
+
+int js2t_plan_get_out_rows(const js2t_plan* plan, int64_t* first_row_out) {
+  if (plan == nullptr || first_row_out == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
+  for (int u = 0; u < plan->n_utts; ++u) first_row_out[u] = plan->h_utts[u].out_row;
+  return JS2T_OK;
+}
+
+int js2t_plan_set_cmvn(js2t_plan* plan, int mode, int norm_means, int norm_vars, int before) {
+  if (plan == nullptr) return fail(JS2T_ERR_INVALID, "NULL plan");
+  if (mode < JS2T_CMVN_NONE || mode > JS2T_CMVN_STATS_ONLY)
+    return fail(JS2T_ERR_INVALID, "unknown CMVN mode %d", mode);
+  plan->cmvn_mode = mode;
+  plan->norm_means = norm_means != 0;
+  plan->norm_vars = norm_vars != 0;
+  plan->before = before != 0;
+  return JS2T_OK;
+}
+
+int js2t_plan_set_global_stats(js2t_plan* plan, const double* mean80, const double* istd80, void* stream) {
+  if (plan == nullptr || mean80 == nullptr || istd80 == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
+  float h[2 * kMel];
+  for (int b = 0; b < kMel; ++b) {
+    h[b] = (float)mean80[b];
+    h[kMel + b] = (float)istd80[b];
+  }
+  JS2T_CUDA(cudaSetDevice(plan->ctx->device));
+  JS2T_CUDA(cudaMemcpyAsync(plan->d_gmean, h, sizeof(h), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  JS2T_CUDA(cudaStreamSynchronize((cudaStream_t)stream));  // h is on the stack
+  plan->global_stats_set = true;
+  return JS2T_OK;
+}
+
+int js2t_plan_set_masks(js2t_plan* plan, int n_fmask, int n_tmask, const int32_t* table, int value_mode,
+                        float value_const, void* stream) {
+  if (plan == nullptr) return fail(JS2T_ERR_INVALID, "NULL plan");
+  if (table == nullptr || n_fmask + n_tmask == 0) {
+    plan->has_masks = false;
+    plan->n_fmask = plan->n_tmask = 0;
+    return JS2T_OK;
+  }
+  if (n_fmask < 0 || n_tmask < 0) return fail(JS2T_ERR_INVALID, "negative mask count");
+  if (value_mode != JS2T_MASK_VALUE_MEAN && value_mode != JS2T_MASK_VALUE_CONST)
+    return fail(JS2T_ERR_INVALID, "unknown mask value mode %d", value_mode);
+  const size_t bytes = sizeof(int32_t) * 2 * (size_t)(n_fmask + n_tmask) * plan->n_utts;
+  JS2T_CUDA(cudaSetDevice(plan->ctx->device));
+  if (bytes > plan->masks_cap) {
+    if (plan->d_masks) cudaFree(plan->d_masks);
+    plan->d_masks = nullptr;
+    plan->masks_cap = 0;
+    JS2T_CUDA(cudaMalloc(&plan->d_masks, bytes));
+    plan->masks_cap = bytes;
+  }
+  JS2T_CUDA(cudaMemcpyAsync(plan->d_masks, table, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  plan->n_fmask = n_fmask;
+  plan->n_tmask = n_tmask;
+  plan->mask_value_mode = value_mode;
+  plan->mask_value_const = value_const;
+  plan->has_masks = true;
+  return JS2T_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static DeviceTables tables_of(const js2t_ctx* c) {
+  DeviceTables t;
+  t.window_half = c->d_tables;
+  t.tw256 = reinterpret_cast<const float2*>(c->d_tables + 400);
+  t.tw512 = reinterpret_cast<const float2*>(c->d_tables + 400 + 512);
+  return t;
+}
+
+static ApplyLaunch make_apply(const js2t_plan* plan, float* out_dev, bool shared) {
+  ApplyLaunch a;
+  a.utts = plan->d_utts;
+  a.tiles = plan->d_tiles;
+  a.n_tiles = plan->n_tiles;
+  a.out = out_dev;
+  a.mean = shared ? plan->d_gmean : plan->d_mean;
+  a.istd = shared ? plan->d_gistd : plan->d_istd;
+  a.shared_stats = shared ? 1 : 0;
+  a.masks = plan->has_masks ? plan->d_masks : nullptr;
+  a.n_fmask = plan->n_fmask;
+  a.n_tmask = plan->n_tmask;
+  a.mask_value = plan->d_mask_value;
+  a.cmvn_after = (plan->cmvn_mode != JS2T_CMVN_NONE && !plan->before) ? 1 : 0;
+  a.pad_tmax = plan->pad_tmax;
+  a.pad_value = plan->pad_value;
+  return a;
+}
+
+static FinalizeLaunch make_finalize(const js2t_plan* plan, const float* raw, bool shared) {
+  FinalizeLaunch z;
+  memset(&z, 0, sizeof(z));
+  z.utts = plan->d_utts;
+  z.n_utts = plan->n_utts;
+  z.tile_stats = plan->d_tile_stats;
+  z.raw = raw;
+  z.norm_means = plan->norm_means;
+  z.norm_vars = plan->norm_vars;
+  z.cmvn_enabled = (plan->cmvn_mode == JS2T_CMVN_UTTERANCE || plan->cmvn_mode == JS2T_CMVN_GLOBAL) ? 1 : 0;
+  z.cmvn_after = plan->before ? 0 : 1;
+  z.g_mean = shared ? plan->d_gmean : nullptr;
+  z.g_istd = shared ? plan->d_gistd : nullptr;
+  z.masks = plan->has_masks ? plan->d_masks : nullptr;
+  z.n_fmask = plan->n_fmask;
+  z.n_tmask = plan->n_tmask;
+  z.mask_value_mode = plan->mask_value_mode;
+  z.mask_value_const = plan->mask_value_const;
+  z.mean = plan->d_mean;
+  z.istd = plan->d_istd;
+  z.mask_value = plan->d_mask_value;
+  z.stats_out = plan->d_utt_stats;
+  return z;
+}
+
+// in_dev (PCM or feature rows) -> out_dev according to the plan
+static int run_pipeline(js2t_plan* plan, const void* in_dev, float* out_dev, cudaStream_t stream,
+                        bool from_pcm) {
+  if (plan == nullptr || in_dev == nullptr || out_dev == nullptr)
+    return fail(JS2T_ERR_INVALID, "execute: NULL argument");
+  if (from_pcm != !plan->feature_input)
+    return fail(JS2T_ERR_STATE, from_pcm ? "js2t_fbank_execute needs a plan made by js2t_plan_create"
+                                         : "js2t_features_execute needs a plan made by js2t_plan_create_features");
+  if (from_pcm && !plan->ctx->tables_set)
+    return fail(JS2T_ERR_STATE, "js2t_ctx_set_tables has not been called");
+  JS2T_CUDA(cudaSetDevice(plan->ctx->device));
+  const int mode = plan->cmvn_mode;
+  const bool masks = plan->has_masks;
+  if (mode == JS2T_CMVN_GLOBAL && !plan->global_stats_set)
+    return fail(JS2T_ERR_STATE, "global CMVN requested but no statistics were set");
+
+  FbankLaunch f;
+  memset(&f, 0, sizeof(f));
+  f.pcm = static_cast<const uint8_t*>(in_dev);
+  f.utts = plan->d_utts;
+  f.tiles = plan->d_tiles;
+  f.n_tiles = plan->n_tiles;
+  if (from_pcm) f.tab = tables_of(plan->ctx);
+  f.out = out_dev;
+  f.pad_tmax = plan->pad_tmax;
+  f.pad_value = plan->pad_value;
+  f.epilogue = kEpiRaw;
+
+  // the dominant kernel, optionally bracketed by profiling events on the launching stream
+  auto launch_main = [&](const FbankLaunch& fl) -> cudaError_t {
+    const size_t slots = plan->prof_ev.size() / 2;
+    const size_t slot = slots ? (size_t)(plan->prof_calls % (long long)slots) : 0;
+    if (slots) cudaEventRecord(plan->prof_ev[2 * slot], stream);
+    cudaError_t e = from_pcm ? launch_fbank(fl, stream) : launch_features(fl, stream);
+    if (slots) {
+      cudaEventRecord(plan->prof_ev[2 * slot + 1], stream);
+      plan->prof_calls++;
+    }
+    return e;
+  };
+  // (1) nothing data-dependent after the log-mel: one kernel, one pass over HBM
+  if (mode == JS2T_CMVN_NONE && !masks) {
+    JS2T_CUDA(launch_main(f));
+    plan->stats_valid = false;
+    return JS2T_OK;
+  }
+  // (2) global CMVN with known statistics and no data-dependent fill value: normalise (+ mask) in
+  //     the fbank epilogue, still one pass
+  const bool mean_fill = masks && plan->mask_value_mode == JS2T_MASK_VALUE_MEAN;
+  if (from_pcm && mode == JS2T_CMVN_GLOBAL && !mean_fill && plan->before) {
+    f.epilogue = kEpiNormKnown;
+    f.g_mean = plan->d_gmean;
+    f.g_istd = plan->d_gistd;
+    if (masks) {
+      f.masks = plan->d_masks;
+      f.n_fmask = plan->n_fmask;
+      f.n_tmask = plan->n_tmask;
+      JS2T_CUDA(launch_fill_value(plan->d_mask_value, plan->n_utts, plan->mask_value_const, stream));
+      f.mask_value = plan->d_mask_value;
+    }
+    JS2T_CUDA(launch_main(f));
+    plan->stats_valid = false;
+    return JS2T_OK;
+  }
+  // (3) raw log-mel + per-tile statistics -> per-utterance finalize -> in-place apply
+  f.tile_stats = plan->d_tile_stats;
+  JS2T_CUDA(launch_main(f));
+  const bool shared = (mode == JS2T_CMVN_GLOBAL);
+  FinalizeLaunch z = make_finalize(plan, out_dev, shared);
+  JS2T_CUDA(launch_finalize(z, stream));
+  plan->stats_valid = true;
+  if (mode == JS2T_CMVN_STATS_ONLY) return JS2T_OK;
+  ApplyLaunch a = make_apply(plan, out_dev, shared);
+  JS2T_CUDA(launch_apply(a, stream));
+  return JS2T_OK;
+}
+
+int js2t_fbank_execute(js2t_plan* plan, const void* pcm_dev, float* out_dev, void* stream) {
+  return run_pipeline(plan, pcm_dev, out_dev, (cudaStream_t)stream, /*from_pcm=*/true);
+}
+
+int js2t_features_execute(js2t_plan* plan, const float* feats_dev, float* out_dev, void* stream) {
+  return run_pipeline(plan, feats_dev, out_dev, (cudaStream_t)stream, /*from_pcm=*/false);
+}
+
+int js2t_plan_enable_profiling(js2t_plan* plan, int n_slots) {
+  if (plan == nullptr || n_slots < 0) return fail(JS2T_ERR_INVALID, "bad argument");
+  JS2T_CUDA(cudaSetDevice(plan->ctx->device));
+  for (cudaEvent_t e : plan->prof_ev) cudaEventDestroy(e);
+  plan->prof_ev.clear();
+  plan->prof_calls = 0;
+  for (int i = 0; i < 2 * n_slots; ++i) {
+    cudaEvent_t e;
+    JS2T_CUDA(cudaEventCreate(&e));
+    plan->prof_ev.push_back(e);
+  }
+  return JS2T_OK;
+}
+
+int js2t_plan_kernel_times_ms(js2t_plan* plan, float* ms_out, int n, int* n_written) {
+  if (plan == nullptr || ms_out == nullptr || n_written == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
+  const long long slots = (long long)plan->prof_ev.size() / 2;
+  const long long have = plan->prof_calls < slots ? plan->prof_calls : slots;
+  int w = 0;
+  for (long long i = 0; i < have && w < n; ++i) {
+    float ms = 0.f;
+    JS2T_CUDA(cudaEventSynchronize(plan->prof_ev[2 * i + 1]));
+    JS2T_CUDA(cudaEventElapsedTime(&ms, plan->prof_ev[2 * i], plan->prof_ev[2 * i + 1]));
+    ms_out[w++] = ms;
+  }
+  *n_written = w;
+  return JS2T_OK;
+}
+
+int js2t_plan_utt_stats(const js2t_plan* plan, const double** stats_dev) {
+  if (plan == nullptr || stats_dev == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
+  if (!plan->stats_valid) return fail(JS2T_ERR_STATE, "no statistics: run js2t_fbank_execute in a statistics mode first");
+  *stats_dev = plan->d_utt_stats;
+  return JS2T_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int js2t_global_stats_accumulate(js2t_plan* plan, double* accum_dev, void* stream) {
+  if (plan == nullptr || accum_dev == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
+  if (!plan->stats_valid) return fail(JS2T_ERR_STATE, "no statistics to accumulate");
+  JS2T_CUDA(cudaSetDevice(plan->ctx->device));
+  JS2T_CUDA(launch_global_accumulate(plan->d_utt_stats, plan->d_utts, plan->n_utts, accum_dev,
+                                     (cudaStream_t)stream));
+  return JS2T_OK;
+}
+
+int js2t_global_stats_allreduce(void* nccl_comm, double* accum_dev, void* stream) {
+  if (nccl_comm == nullptr || accum_dev == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
+  // ncclResult_t ncclAllReduce(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t)
+  typedef int (*allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  static allreduce_fn fn = nullptr;
+  if (fn == nullptr) {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (h == nullptr) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h == nullptr) return fail(JS2T_ERR_NCCL, "cannot load libnccl: %s", dlerror());
+    fn = reinterpret_cast<allreduce_fn>(dlsym(h, "ncclAllReduce"));
+    if (fn == nullptr) return fail(JS2T_ERR_NCCL, "ncclAllReduce not found in libnccl");
+  }
+  const int kNcclFloat64 = 8, kNcclSum = 0;
+  const int rc = fn(accum_dev, accum_dev, (size_t)(kStatsPerTile + 1), kNcclFloat64, kNcclSum, nccl_comm,
+                    (cudaStream_t)stream);
+  if (rc != 0) return fail(JS2T_ERR_NCCL, "ncclAllReduce failed with code %d", rc);
+  return JS2T_OK;
+}
+
+int js2t_global_stats_finalize(js2t_plan* plan, const double* accum_dev, void* stream) {
+  if (plan == nullptr || accum_dev == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
+  JS2T_CUDA(cudaSetDevice(plan->ctx->device));
+  JS2T_CUDA(launch_global_finalize(accum_dev, plan->norm_means, plan->norm_vars, plan->d_gmean, plan->d_gistd,
+                                   (cudaStream_t)stream));
+  plan->global_stats_set = true;
+  return JS2T_OK;
+}
+
+int js2t_normalize_execute(js2t_plan* plan, float* out_dev, void* stream_) {
+  if (plan == nullptr || out_dev == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
+  if (!plan->global_stats_set) return fail(JS2T_ERR_STATE, "no global statistics set");
+  if (!plan->stats_valid)
+    return fail(JS2T_ERR_STATE, "js2t_normalize_execute follows a STATS_ONLY js2t_fbank_execute on the same plan");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  JS2T_CUDA(cudaSetDevice(plan->ctx->device));
+  const int saved = plan->cmvn_mode;
+  plan->cmvn_mode = JS2T_CMVN_GLOBAL;
+  // per-utterance fill value under the global normalisation (re-reads the per-tile statistics)
+  FinalizeLaunch z = make_finalize(plan, out_dev, /*shared=*/true);
+  cudaError_t e = launch_finalize(z, stream);
+  ApplyLaunch a = make_apply(plan, out_dev, /*shared=*/true);
+  if (e == cudaSuccess) e = launch_apply(a, stream);
+  plan->cmvn_mode = saved;
+  JS2T_CUDA(e);
+  return JS2T_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,332 @@
+# coding: utf-8
+"""
+Batched host API of the B200 front-end: ragged batch of waveforms (or pre-extracted features) in,
+``(sum T, 80)`` / ``(B, Tmax, 80)`` CUDA tensor out, through the C ABI of
+``include/joeys2t_b200.h``.  torch is used for device memory, pinned staging and streams only.
+
+The per-item wrappers with the reference's signatures (``helpers_for_audio.py``,
+``data_augmentation.py``, ``speech_processor.py``) are batch-of-one calls into this module.
+"""
+import ctypes
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from joeys2t_b200 import _lib, tables
+
+NUM_MEL = tables.NUM_MEL_BINS
+Array = Union[np.ndarray, torch.Tensor]
+
+_contexts = {}
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "joeys2t_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+
+
+def _stream_ptr(stream: Optional[torch.cuda.Stream] = None) -> int:
+    return (stream or torch.cuda.current_stream()).cuda_stream
+
+
+class Context:
+    """One per device: owns the window / twiddle / mel tables (``js2t_ctx``)."""
+
+    def __init__(self, device: int):
+        _require_cuda()
+        lib = _lib.load()
+        self.device = device
+        self._h = ctypes.c_void_p()
+        _lib.check(lib.js2t_ctx_create(device, ctypes.byref(self._h)))
+        win = np.ascontiguousarray(tables.povey_window(), np.float32)
+        mel = np.ascontiguousarray(tables.mel_banks(NUM_MEL), np.float32)
+        _lib.check(lib.js2t_ctx_set_tables(self._h, win.ctypes.data, mel.ctypes.data))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.load().js2t_ctx_destroy(self._h)
+        except Exception:  # pylint: disable=broad-except
+            pass
+
+
+def get_context(device: Optional[int] = None) -> Context:
+    _require_cuda()
+    if device is None:
+        device = torch.cuda.current_device()
+    if device not in _contexts:
+        _contexts[device] = Context(device)
+    return _contexts[device]
+
+
+# ------------------------------------------------------------------------------------------
+# packing
+# ------------------------------------------------------------------------------------------
+def _as_1d_pcm(w: Array) -> np.ndarray:
+    """→ 1-D int16 or float32 numpy array, channel 0 of multi-channel input (quirk Q1:
+    ``helpers_for_audio.py:53-54`` discards the mono mix and torchaudio takes row 0)."""
+    if isinstance(w, torch.Tensor):
+        w = w.detach().cpu().numpy()
+    w = np.asarray(w)
+    if w.ndim == 2:
+        w = w[0]
+    if w.ndim != 1:
+        raise ValueError(f"waveform must be (C, N) or (N,), got shape {w.shape}")
+    if w.dtype == np.int16:
+        return np.ascontiguousarray(w)
+    # the kernels compute in float32 (quirk Q3: float64 input is rounded to float32 first)
+    return np.ascontiguousarray(w, dtype=np.float32)
+
+
+class PackedPCM:
+    """Ragged batch packed into one pinned byte buffer, every utterance 16-byte aligned."""
+
+    def __init__(self, waveforms: Sequence[Array]):
+        arrs = [_as_1d_pcm(w) for w in waveforms]
+        self.n_samples = np.array([a.shape[0] for a in arrs], np.int64)
+        self.is_f32 = np.array([a.dtype != np.int16 for a in arrs], np.uint8)
+        sizes = np.array([a.nbytes for a in arrs], np.int64)
+        aligned = (sizes + 15) // 16 * 16
+        self.byte_off = np.concatenate([[0], np.cumsum(aligned)[:-1]]).astype(np.int64)
+        self.nbytes = int(aligned.sum())
+        pin = torch.cuda.is_available()
+        self.host = torch.empty(max(self.nbytes, 16), dtype=torch.uint8, pin_memory=pin)
+        hv = self.host.numpy()
+        for a, o in zip(arrs, self.byte_off):
+            hv[o:o + a.nbytes] = a.view(np.uint8)
+
+    def to_device(self, device=None, non_blocking: bool = True) -> torch.Tensor:
+        return self.host.to(device or "cuda", non_blocking=non_blocking)
+
+
+# ------------------------------------------------------------------------------------------
+# plan
+# ------------------------------------------------------------------------------------------
+class Plan:
+    """Geometry + workspace of one ragged batch (``js2t_plan``)."""
+
+    def __init__(self, n_samples=None, byte_off=None, is_f32=None, *, n_frames_in=None,
+                 max_frames=None, layout: str = "ragged", pad_tmax: int = 0,
+                 pad_value: float = 1.0, device: Optional[int] = None):
+        self.ctx = get_context(device)
+        lib = _lib.load()
+        self._lib = lib
+        self._h = ctypes.c_void_p()
+        lay = {"ragged": _lib.LAYOUT_RAGGED, "padded": _lib.LAYOUT_PADDED}[layout]
+        self.layout = layout
+        mf = None if max_frames is None else np.ascontiguousarray(max_frames, np.int32)
+        mf_p = None if mf is None else mf.ctypes.data
+        if n_frames_in is not None:
+            nfi = np.ascontiguousarray(n_frames_in, np.int32)
+            self.n_utts = len(nfi)
+            _lib.check(lib.js2t_plan_create_features(self.ctx.handle, self.n_utts, nfi.ctypes.data,
+                                                     mf_p, lay, int(pad_tmax), float(pad_value),
+                                                     ctypes.byref(self._h)))
+            self.feature_input = True
+        else:
+            ns = np.ascontiguousarray(n_samples, np.int64)
+            bo = np.ascontiguousarray(byte_off, np.int64)
+            f32 = np.ascontiguousarray(
+                np.zeros(len(ns), np.uint8) if is_f32 is None else is_f32, np.uint8)
+            self.n_utts = len(ns)
+            _lib.check(lib.js2t_plan_create(self.ctx.handle, self.n_utts, bo.ctypes.data,
+                                            ns.ctypes.data, f32.ctypes.data, mf_p, lay,
+                                            int(pad_tmax), float(pad_value),
+                                            ctypes.byref(self._h)))
+            self.feature_input = False
+        self.total_frames = int(lib.js2t_plan_total_frames(self._h))
+        self.out_rows = int(lib.js2t_plan_out_rows(self._h))
+        nf = np.zeros(self.n_utts, np.int32)
+        _lib.check(lib.js2t_plan_get_frames(self._h, nf.ctypes.data))
+        self.n_frames = nf
+        rows = np.zeros(self.n_utts, np.int64)
+        _lib.check(lib.js2t_plan_get_out_rows(self._h, rows.ctypes.data))
+        self.out_row = rows
+        self.pad_tmax = self.out_rows // self.n_utts if layout == "padded" else 0
+        self._keepalive = None
+
+    # ---- configuration ----------------------------------------------------------------------
+    def set_cmvn(self, mode: str = "utterance", norm_means: bool = True, norm_vars: bool = True,
+                 before: bool = True) -> "Plan":
+        m = {"none": _lib.CMVN_NONE, "utterance": _lib.CMVN_UTTERANCE, "global": _lib.CMVN_GLOBAL,
+             "stats": _lib.CMVN_STATS_ONLY}[mode]
+        _lib.check(self._lib.js2t_plan_set_cmvn(self._h, m, int(norm_means), int(norm_vars),
+                                                int(before)))
+        return self
+
+    def set_global_stats(self, mean: np.ndarray, istd: np.ndarray) -> "Plan":
+        mean = np.ascontiguousarray(mean, np.float64)
+        istd = np.ascontiguousarray(istd, np.float64)
+        assert mean.shape == (NUM_MEL,) and istd.shape == (NUM_MEL,)
+        _lib.check(self._lib.js2t_plan_set_global_stats(self._h, mean.ctypes.data, istd.ctypes.data,
+                                                        _stream_ptr()))
+        return self
+
+    def set_masks(self, table: Optional[np.ndarray], n_fmask: int = 0, n_tmask: int = 0,
+                  mask_value: Optional[float] = None) -> "Plan":
+        """``table``: int32 (B, n_fmask + n_tmask, 2) = (start, width), frequency masks first."""
+        if table is None:
+            _lib.check(self._lib.js2t_plan_set_masks(self._h, 0, 0, None, 0, 0.0, _stream_ptr()))
+            return self
+        t = np.ascontiguousarray(table, np.int32)
+        assert t.shape == (self.n_utts, n_fmask + n_tmask, 2), t.shape
+        mode = _lib.MASK_VALUE_MEAN if mask_value is None else _lib.MASK_VALUE_CONST
+        _lib.check(self._lib.js2t_plan_set_masks(self._h, n_fmask, n_tmask, t.ctypes.data, mode,
+                                                 0.0 if mask_value is None else float(mask_value),
+                                                 _stream_ptr()))
+        torch.cuda.current_stream().synchronize()  # table is pageable host memory
+        return self
+
+    # ---- execution --------------------------------------------------------------------------
+    def empty_output(self) -> torch.Tensor:
+        shape = (self.n_utts, self.pad_tmax, NUM_MEL) if self.layout == "padded" else \
+            (self.out_rows, NUM_MEL)
+        return torch.empty(shape, dtype=torch.float32, device=f"cuda:{self.ctx.device}")
+
+    def execute(self, src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """PCM bytes (or feature rows for a feature plan) on the device → features on the device.
+        Asynchronous on the current stream."""
+        assert src.is_cuda and src.is_contiguous()
+        if out is None:
+            out = self.empty_output()
+        assert out.is_cuda and out.is_contiguous() and out.dtype == torch.float32
+        assert out.numel() >= self.out_rows * NUM_MEL
+        fn = self._lib.js2t_features_execute if self.feature_input else self._lib.js2t_fbank_execute
+        _lib.check(fn(self._h, src.data_ptr(), out.data_ptr(), _stream_ptr()))
+        return out
+
+    def enable_profiling(self, n_slots: int) -> None:
+        _lib.check(self._lib.js2t_plan_enable_profiling(self._h, int(n_slots)))
+
+    def kernel_times_ms(self, n: int) -> np.ndarray:
+        """Durations of the fbank kernel of the profiled executes (synchronises on their events)."""
+        buf = np.zeros(n, np.float32)
+        got = ctypes.c_int(0)
+        _lib.check(self._lib.js2t_plan_kernel_times_ms(self._h, buf.ctypes.data, n, ctypes.byref(got)))
+        return buf[:got.value]
+
+    def utt_stats(self) -> torch.Tensor:
+        """(B, 160) float64 per-utterance sum | sum of squares of the raw log-mel (a device copy)."""
+        p = ctypes.c_void_p()
+        _lib.check(self._lib.js2t_plan_utt_stats(self._h, ctypes.byref(p)))
+        out = torch.empty((self.n_utts, 2 * NUM_MEL), dtype=torch.float64,
+                          device=f"cuda:{self.ctx.device}")
+        rc = torch.cuda.cudart().cudaMemcpyAsync(out.data_ptr(), p.value, out.numel() * 8, 3,
+                                                 _stream_ptr())
+        if int(rc) != 0:
+            raise RuntimeError(f"cudaMemcpyAsync failed: {rc}")
+        return out
+
+    def accumulate_global(self, accum: torch.Tensor) -> None:
+        """accum (161,) float64 cuda: sum[80] | sumsq[80] | frames  += this batch."""
+        assert accum.is_cuda and accum.dtype == torch.float64 and accum.numel() == 2 * NUM_MEL + 1
+        _lib.check(self._lib.js2t_global_stats_accumulate(self._h, accum.data_ptr(), _stream_ptr()))
+
+    def finalize_global(self, accum: torch.Tensor) -> None:
+        _lib.check(self._lib.js2t_global_stats_finalize(self._h, accum.data_ptr(), _stream_ptr()))
+
+    def normalize(self, out: torch.Tensor) -> torch.Tensor:
+        _lib.check(self._lib.js2t_normalize_execute(self._h, out.data_ptr(), _stream_ptr()))
+        return out
+
+    def split(self, out: torch.Tensor) -> List[torch.Tensor]:
+        """Views of the per-utterance (T_u, 80) blocks of an output tensor."""
+        flat = out.reshape(-1, NUM_MEL)
+        return [flat[r:r + t] for r, t in zip(self.out_row.tolist(), self.n_frames.tolist())]
+
+    def close(self):
+        if self._h:
+            self._lib.js2t_plan_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass
+
+
+# ------------------------------------------------------------------------------------------
+# one-call batched entry point
+# ------------------------------------------------------------------------------------------
+def fbank_cmvn_specaug_ragged(
+    waveforms: Sequence[Array],
+    *,
+    cmvn: Optional[dict] = None,
+    masks: Optional[np.ndarray] = None,
+    n_fmask: int = 0,
+    n_tmask: int = 0,
+    mask_value: Optional[float] = None,
+    max_frames: Optional[Sequence[int]] = None,
+    layout: str = "ragged",
+    pad_value: float = 1.0,
+    global_stats: Optional[Tuple[np.ndarray, np.ndarray]] = None,
+) -> Tuple[torch.Tensor, np.ndarray]:
+    """Whole batch in one call: pack → H2D → fbank [→ CMVN] [→ SpecAugment] on the GPU.
+
+    :param waveforms: list of (C, N) / (N,) arrays; int16 PCM, or float in [-1, 1) as produced by
+        ``torchaudio.load`` (scaled by 2**15 on the device, ``helpers_for_audio.py:54``)
+    :param cmvn: ``{"norm_means", "norm_vars", "before"}`` like the reference's ``CMVN(**cfg)``;
+        ``None`` = raw log-mel
+    :param masks: int32 (B, n_fmask + n_tmask, 2) host-drawn SpecAugment table (see
+        :func:`joeys2t_b200.data_augmentation.draw_masks`)
+    :returns: (features on the GPU — ragged ``(sum T, 80)`` or padded ``(B, Tmax, 80)`` —, n_frames)
+    """
+    packed = PackedPCM(waveforms)
+    plan = Plan(packed.n_samples, packed.byte_off, packed.is_f32, max_frames=max_frames,
+                layout=layout, pad_value=pad_value)
+    if global_stats is not None:
+        kw = dict(cmvn or {})
+        plan.set_cmvn("global", kw.get("norm_means", True), kw.get("norm_vars", True),
+                      kw.get("before", True))
+        plan.set_global_stats(*global_stats)
+    elif cmvn is not None:
+        plan.set_cmvn("utterance", cmvn.get("norm_means", True), cmvn.get("norm_vars", True),
+                      cmvn.get("before", True))
+    if masks is not None:
+        plan.set_masks(masks, n_fmask, n_tmask, mask_value)
+    out = plan.execute(packed.to_device(f"cuda:{plan.ctx.device}"))
+    n_frames = plan.n_frames.copy()
+    # the plan's workspace must outlive the enqueued kernels
+    torch.cuda.current_stream().synchronize()
+    plan.close()
+    return out, n_frames
+
+
+def features_cmvn_specaug_ragged(
+    feats: Sequence[np.ndarray],
+    *,
+    cmvn: Optional[dict] = None,
+    masks: Optional[np.ndarray] = None,
+    n_fmask: int = 0,
+    n_tmask: int = 0,
+    mask_value: Optional[float] = None,
+    max_frames: Optional[Sequence[int]] = None,
+    layout: str = "ragged",
+    pad_value: float = 1.0,
+) -> Tuple[torch.Tensor, np.ndarray]:
+    """Same for pre-extracted (T, 80) feature matrices (the .npy / zip branch of ``get_features``)."""
+    arrs = [np.ascontiguousarray(f, np.float32) for f in feats]
+    for a in arrs:
+        if a.ndim != 2 or a.shape[1] != NUM_MEL:
+            raise ValueError(f"features must be (T, {NUM_MEL}); got {a.shape}")
+    n_in = np.array([a.shape[0] for a in arrs], np.int32)
+    host = torch.empty((int(n_in.sum()), NUM_MEL), dtype=torch.float32, pin_memory=True)
+    np.concatenate(arrs, 0, out=host.numpy())
+    plan = Plan(n_frames_in=n_in, max_frames=max_frames, layout=layout, pad_value=pad_value)
+    if cmvn is not None:
+        plan.set_cmvn("utterance", cmvn.get("norm_means", True), cmvn.get("norm_vars", True),
+                      cmvn.get("before", True))
+    if masks is not None:
+        plan.set_masks(masks, n_fmask, n_tmask, mask_value)
+    out = plan.execute(host.to(f"cuda:{plan.ctx.device}", non_blocking=True))
+    n_frames = plan.n_frames.copy()
+    torch.cuda.current_stream().synchronize()
+    plan.close()
+    return out, n_frames

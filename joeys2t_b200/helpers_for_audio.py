@@ -1,0 +1,198 @@
+# coding: utf-8
+"""
+Collection of helper functions for audio processing — B200 drop-in for
+``joeynmt/helpers_for_audio.py`` (same function names, arguments and return containers).
+
+``extract_fbank_features`` / ``_get_torchaudio_fbank`` run the hand-written CUDA front-end instead of
+``torchaudio.compliance.kaldi.fbank`` on the CPU; everything else (``.npy`` cache, npy-in-zip reader,
+``get_n_frames``, ``pad_features``) keeps the reference's behaviour on the host.
+
+Deliberate deviations:
+
+* Q2: a too-short waveform raises ``ValueError`` whether or not ``output_path`` is given (the
+  reference's f-string crashes with ``AttributeError`` when ``output_path is None``,
+  helpers_for_audio.py:58-62).
+* Q3: the result is always float32 (the reference returns float64 for float64 input).
+* Q7: only 16 kHz is supported (all shipped configs and fixtures are 16 kHz); other rates raise.
+* only ``n_mel_bins == 80`` (``num_freq: 80`` in every shipped config).
+"""
+import io
+import wave
+from pathlib import Path
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from joeys2t_b200 import frontend, tables
+
+
+# from fairseq (kept for API parity; like the reference, its result is not used downstream:
+# helpers_for_audio.py:53-54 overwrites it, and the fbank then reads channel 0)
+def _convert_to_mono(waveform: torch.FloatTensor, sample_rate: int) -> torch.FloatTensor:
+    if waveform.shape[0] > 1:
+        return waveform.mean(0, keepdim=True)
+    return waveform
+
+
+def _check_config(sample_rate: int, n_bins: int):
+    if int(sample_rate) != tables.SAMPLE_RATE:
+        raise ValueError(
+            f"joeys2t_b200 front-end is specialised for {tables.SAMPLE_RATE} Hz audio; "
+            f"got sample_rate={sample_rate}. Resample first (no CPU fallback).")
+    if int(n_bins) != tables.NUM_MEL_BINS:
+        raise ValueError(
+            f"joeys2t_b200 front-end is specialised for {tables.NUM_MEL_BINS} mel bins; got {n_bins}.")
+
+
+def _get_torchaudio_fbank(waveform, sample_rate: int, n_bins: int = 80) -> np.ndarray:
+    """Kaldi-compatible mel filter bank features of an **int16-range** waveform
+    (helpers_for_audio.py:30-37: ``ta_kaldi.fbank(waveform, num_mel_bins, sample_frequency)``)."""
+    _check_config(sample_rate, n_bins)
+    w = waveform.detach().cpu().numpy() if isinstance(waveform, torch.Tensor) else np.asarray(waveform)
+    if w.ndim == 2:
+        w = w[0]
+    if w.dtype != np.int16:
+        # the device path scales float PCM by 2**15 itself; undo the caller's scaling exactly
+        w = (w.astype(np.float32) * np.float32(2.0**-15))
+    feats, _ = frontend.fbank_cmvn_specaug_ragged([w])
+    return feats.cpu().numpy()
+
+
+def extract_fbank_features(
+    waveform: torch.FloatTensor,
+    sample_rate: int,
+    output_path: Optional[Path] = None,
+    n_mel_bins: int = 80,
+    overwrite: bool = False
+) -> Optional[np.ndarray]:
+    """helpers_for_audio.py:41-68.  ``waveform`` is (C, N) in [-1, 1) as returned by
+    ``torchaudio.load`` (int16 PCM tensors/arrays are accepted too and used as they are)."""
+    # pylint: disable=inconsistent-return-statements
+    if output_path is not None and output_path.is_file() and not overwrite:
+        return np.load(output_path.as_posix())
+
+    try:
+        _check_config(sample_rate, n_mel_bins)
+        features, _ = frontend.fbank_cmvn_specaug_ragged([waveform])
+        features = features.cpu().numpy()
+    except Exception as e:
+        stem = output_path.stem if output_path is not None else "<memory>"
+        raise ValueError(
+            f"torchaudio faild to extract mel filterbank features "
+            f"at: {stem}. {e}"
+        ) from e
+
+    if output_path is not None:
+        np.save(output_path.as_posix(), features)
+        assert output_path.is_file(), output_path
+
+    return features
+
+
+# from fairseq
+def _is_npy_data(data: bytes) -> bool:
+    return data[0] == 147 and data[1] == 78
+
+
+# from fairseq
+def _get_features_from_zip(path, byte_offset, byte_size):
+    with path.open("rb") as f:
+        f.seek(byte_offset)
+        data = f.read(byte_size)
+    byte_features = io.BytesIO(data)
+    if len(data) > 1 and _is_npy_data(data):
+        features = np.load(byte_features)
+    else:
+        raise ValueError(
+            f'Unknown file format for '
+            f'"{path}" [{byte_offset}:{byte_size}]'
+        )
+    return features
+
+
+# from fairseq
+def get_n_frames(wave_length: int, sample_rate: int):
+    duration_ms = int(wave_length / sample_rate * 1000)
+    n_frames = int(1 + (duration_ms - 25) / 10)
+    return n_frames
+
+
+def load_waveform(path: Path) -> Tuple[np.ndarray, int]:
+    """PCM ingest for ``get_features`` (helpers_for_audio.py:115 uses ``torchaudio.load``).
+
+    16-bit PCM WAV is read with the stdlib and kept as int16 — bit-identical to the reference's
+    ``/32768 … *2**15`` round trip (quirk Q4).  Anything else goes through ``torchaudio.load``.
+    """
+    if path.suffix == ".wav":
+        try:
+            with wave.open(path.as_posix(), "rb") as w:
+                if w.getsampwidth() == 2 and w.getcomptype() == "NONE":
+                    pcm = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2")
+                    pcm = pcm.reshape(-1, w.getnchannels()).T  # (C, N)
+                    return np.ascontiguousarray(pcm), w.getframerate()
+        except wave.Error:
+            pass
+    import torchaudio  # pylint: disable=import-outside-toplevel
+    waveform, sample_rate = torchaudio.load(path.as_posix())
+    return waveform.numpy(), sample_rate
+
+
+def get_features(root_path: Path, fbank_path: str) -> np.ndarray:
+    """Get speech features from a wav/mp3, a .npy, or a ZIP file accessed via byte offset and
+    length — helpers_for_audio.py:100-127.
+
+    :return: (np.ndarray) speech features in shape of (num_frames, num_freq)
+    """
+    _path, *extra = fbank_path.split(":")
+    _path = Path(root_path) / _path
+    if not _path.is_file():
+        raise FileNotFoundError(f"File not found: {_path}")
+
+    if len(extra) == 0:
+        if _path.suffix == ".npy":
+            features = np.load(_path.as_posix())
+        elif _path.suffix in [".mp3", ".wav"]:
+            waveform, sample_rate = load_waveform(_path)
+            features = extract_fbank_features(waveform, sample_rate)
+        else:
+            raise ValueError(f"Invalid file type: {_path}")
+    elif len(extra) == 2:
+        assert _path.suffix == ".zip"
+        extra = [int(i) for i in extra]
+        features = _get_features_from_zip(_path, extra[0], extra[1])
+    else:
+        raise ValueError(f"Invalid path: {root_path / fbank_path}")
+
+    assert len(features.shape) == 2, "spectrogram must be a 2-D array."
+    return features
+
+
+def pad_features(
+    feat_list: List[np.ndarray],
+    embed_size: int = 80,
+    pad_index: int = 1,
+) -> Tuple[np.ndarray, List[int], None]:
+    """
+    Pad continuous feature representation in batch — helpers_for_audio.py:130-170.
+    Host-side (the inputs are host arrays); the batched device path emits this layout directly
+    (``layout="padded"``), so the collate step has nothing left to copy.
+
+    :returns:
+      - features np.ndarray, (batch_size, src_len, embed_size) filled with float(pad_index)
+      - lengths List[int], (batch_size)
+    """
+    max_len = max([int(f.shape[0]) for f in feat_list])
+    batch_size = len(feat_list)
+    features = np.full((batch_size, max_len, embed_size), float(pad_index), dtype=np.float32)
+    lengths = []
+    for i, f in enumerate(feat_list):
+        length = min(int(f.shape[0]), max_len)
+        assert length > 0, "empty feature!"
+        features[i, :length, :] = f[:length, :]
+        lengths.append(length)
+
+    assert max(lengths) == features.shape[1]
+    assert embed_size == features.shape[2]
+    assert sum(lengths) > 0
+    return features, lengths, None

@@ -1,0 +1,392 @@
+# coding: utf-8
+"""
+Parity of the CUDA path (through the C ABI) against the reference's golden vectors and the CPU
+oracle.  ``-m gpu`` only.
+
+Tolerances (BASELINE.json north_star / SURVEY.md §8c):
+  * raw log-mel:            max |Δ| <= 1e-3
+  * CMVN-normalised output: |Δ| <= 5e-4 + 1e-4 |ref|
+  * CMVN arithmetic alone (our CMVN on the reference's log-mel): rtol 1e-4, atol 1e-5
+  * SpecAugment:            masked-cell positions bit-exact, fill value within 1e-6 of the mean
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import fbank_numpy as O  # noqa: E402
+
+LOGMEL_ATOL = 1e-3
+KNOWN_ANSWER = np.array([
+    -1.0788909, -1.0076448, -1.0421542, -1.0393586, -1.0239305,
+    -0.9921213, -0.95107234, -0.9340749, -0.9119267, -0.8962079,
+], np.float32)  # /root/reference/test/unit/test_tokenizer.py:322-329
+
+
+@pytest.fixture(scope="module")
+def fe():
+    if not torch.cuda.is_available():
+        pytest.fail("gpu tests need a CUDA device")
+    from joeys2t_b200 import _lib, frontend
+    if _lib.is_stale():
+        _lib.build()
+    return frontend
+
+
+def cmvn_close(got, ref):
+    err = np.abs(got - ref)
+    tol = 5e-4 + 1e-4 * np.abs(ref)
+    assert (err <= tol).all(), f"max err {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
+# ------------------------------------------------------------------------------------------------
+# config 1: the reference's own fixture wavs
+# ------------------------------------------------------------------------------------------------
+def test_fixture_fbank_vs_reference_golden(fe, fixtures_pcm, ref_fbank):
+    pcm, n_frames = fixtures_pcm
+    out, lens = fe.fbank_cmvn_specaug_ragged(pcm)
+    assert lens.tolist() == n_frames.tolist()
+    got = out.cpu().numpy()
+    off = 0
+    worst = 0.0
+    for i, ref in enumerate(ref_fbank):
+        g = got[off:off + ref.shape[0]]
+        off += ref.shape[0]
+        d = np.abs(g - ref).max()
+        worst = max(worst, d)
+        assert d <= LOGMEL_ATOL, f"clip {i}: {d}"
+    print("fixture log-mel max abs err vs reference", worst)
+
+
+def test_fixture_float32_pcm_path(fe, fixtures_pcm, ref_fbank):
+    pcm, _ = fixtures_pcm
+    waves = [torch.from_numpy(x.astype(np.float32) / 32768.0).unsqueeze(0) for x in pcm[:4]]
+    out, _ = fe.fbank_cmvn_specaug_ragged(waves)
+    ints, _ = fe.fbank_cmvn_specaug_ragged(pcm[:4])
+    # quirk Q4: float PCM * 2**15 is exactly the int16 sample
+    assert torch.equal(out, ints)
+    assert np.abs(out.cpu().numpy()[:215] - ref_fbank[0]).max() <= LOGMEL_ATOL
+
+
+def test_known_answer_vector(fe, fixtures_pcm):
+    pcm, _ = fixtures_pcm
+    out, _ = fe.fbank_cmvn_specaug_ragged([pcm[1]], cmvn=dict(norm_means=True, norm_vars=True))
+    np.testing.assert_allclose(out.cpu().numpy()[0, :10], KNOWN_ANSWER, atol=5e-4, rtol=1e-4)
+
+
+def test_fixture_utterance_cmvn(fe, fixtures_pcm, ref_fbank, ref_cmvn):
+    pcm, _ = fixtures_pcm
+    out, lens = fe.fbank_cmvn_specaug_ragged(pcm, cmvn=dict(norm_means=True, norm_vars=True))
+    got = out.cpu().numpy()
+    off = 0
+    for i, f in enumerate(ref_fbank):
+        g = got[off:off + f.shape[0]]
+        off += f.shape[0]
+        cmvn_close(g, O.cmvn(f))
+        assert np.abs(g[:4] - ref_cmvn[f"m1v1_head{i}"]).max() <= 1e-3
+    cmvn_close(got[215:215 + 172], ref_cmvn["m1v1_full1"])
+
+
+@pytest.mark.parametrize("nm", [True, False])
+@pytest.mark.parametrize("nv", [True, False])
+def test_cmvn_arithmetic_in_isolation(fe, ref_fbank, ref_cmvn, nm, nv):
+    """Our CMVN kernels on the reference's own log-mel (feature-input path)."""
+    tag = f"m{int(nm)}v{int(nv)}"
+    out, lens = fe.features_cmvn_specaug_ragged(ref_fbank, cmvn=dict(norm_means=nm, norm_vars=nv))
+    got = out.cpu().numpy()
+    off = 0
+    for i, f in enumerate(ref_fbank):
+        g = got[off:off + f.shape[0]]
+        off += f.shape[0]
+        # the reference's float32 column sums drift with T (1.3e-4 at T~5000); the fp64
+        # restatement of the same formula is the arbiter for the tight tolerance
+        np.testing.assert_allclose(g, O.cmvn_fp64(f, nm, nv), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(g, O.cmvn(f, nm, nv), rtol=1e-4, atol=2e-4)
+        np.testing.assert_allclose(g[:4], ref_cmvn[f"{tag}_head{i}"], rtol=1e-4, atol=2e-4)
+
+
+def test_cmvn_class_dropin(fe, ref_fbank, ref_cmvn):
+    from joeys2t_b200.data_augmentation import CMVN
+    c = CMVN()
+    assert repr(c) == "CMVN(norm_means=True, norm_vars=True, before=True)" and c.before is True
+    x = ref_fbank[1].copy()
+    y = c(x)
+    assert np.array_equal(x, ref_fbank[1]), "input must not be mutated"
+    assert y.dtype == np.float32 and y.flags["C_CONTIGUOUS"]
+    np.testing.assert_allclose(y, ref_cmvn["m1v1_full1"], rtol=1e-4, atol=1e-4)
+
+
+def test_silent_utterance(fe, ref_cmvn):
+    out, _ = fe.fbank_cmvn_specaug_ragged([np.zeros(4000, np.int16)])
+    assert np.array_equal(out.cpu().numpy(), ref_cmvn["silent_fbank"])
+    out, _ = fe.fbank_cmvn_specaug_ragged([np.zeros(4000, np.int16)], cmvn={})
+    assert np.array_equal(out.cpu().numpy(), ref_cmvn["silent_cmvn"])  # var = 0 -> std = 1e-5 branch
+
+
+# ------------------------------------------------------------------------------------------------
+# SpecAugment: positions bit-exact, fill value = mean of the spectrogram
+# ------------------------------------------------------------------------------------------------
+SA_CFGS = {
+    "mustc": dict(freq_mask_n=2, freq_mask_f=27, time_mask_n=2, time_mask_t=100, time_mask_p=1.0),
+    "test": dict(freq_mask_n=1, freq_mask_f=5, time_mask_n=1, time_mask_t=10, time_mask_p=1.0),
+    "default": dict(),
+    "smallp": dict(freq_mask_n=2, freq_mask_f=27, time_mask_n=2, time_mask_t=100, time_mask_p=0.05),
+    "zerop": dict(freq_mask_n=2, freq_mask_f=27, time_mask_n=2, time_mask_t=100, time_mask_p=0.001),
+    "widef": dict(freq_mask_n=2, freq_mask_f=81, time_mask_n=2, time_mask_t=100, time_mask_p=1.0),
+    "const": dict(freq_mask_n=2, freq_mask_f=27, time_mask_n=2, time_mask_t=100, time_mask_p=1.0,
+                  mask_value=0.0),
+}
+
+
+@pytest.mark.parametrize("cname", list(SA_CFGS))
+def test_specaugment_class_vs_reference_golden(fe, ref_fbank, ref_specaugment, cname):
+    from joeys2t_b200.data_augmentation import SpecAugment
+    g = ref_specaugment
+    cfg = SA_CFGS[cname]
+    sa = SpecAugment(**cfg)
+    for seed in (0, 2345):
+        for i in (1, 0, 9):
+            x = O.cmvn(ref_fbank[i])
+            key = f"{cname}_s{seed}_c{i}"
+            np.random.seed(seed)
+            y = sa(x)
+            assert y.shape == x.shape and y.dtype == np.float32
+            # positions: bit-exact
+            assert np.array_equal(np.packbits(y != x), g[key + "_changed"]), key
+            changed = y != x
+            # untouched cells are bit-identical to the input; filled cells hold the fill value
+            assert np.array_equal(y[~changed], x[~changed])
+            if changed.any():
+                assert np.abs(y[changed] - g[key + "_maskvalue"]).max() <= 1e-6
+            if i == 1:
+                np.testing.assert_allclose(y, g[key + "_full"], rtol=0, atol=1e-6)
+            # the RNG must have been consumed exactly like the reference: next draw agrees
+            nxt = np.random.randint(0, 1 << 30)
+            np.random.seed(seed)
+            O.specaugment(x, **cfg)
+            assert nxt == np.random.randint(0, 1 << 30)
+
+
+def test_fused_fbank_cmvn_specaugment_batch(fe, fixtures_pcm, ref_fbank):
+    """The fused batched path == reference per-item loop (CMVN -> SpecAugment), padded layout."""
+    from joeys2t_b200.data_augmentation import SpecAugment, mask_tables_for_batch
+    pcm, n_frames = fixtures_pcm
+    cfg = SA_CFGS["mustc"]
+    np.random.seed(77)
+    table, nf, nt = mask_tables_for_batch(SpecAugment(**cfg), n_frames)
+    out, lens = fe.fbank_cmvn_specaug_ragged(pcm, cmvn=dict(norm_means=True, norm_vars=True),
+                                             masks=table, n_fmask=nf, n_tmask=nt, layout="padded")
+    got = out.cpu().numpy()
+    assert got.shape == (10, 1470, 80)
+    np.random.seed(77)
+    for u, f in enumerate(ref_fbank):
+        x = O.cmvn(f)
+        ref = O.specaugment(x, **cfg)
+        t = f.shape[0]
+        masked = ref != x
+        cmvn_close(got[u, :t][~masked], ref[~masked])
+        assert np.abs(got[u, :t][masked] - ref[masked]).max(initial=0) <= 1e-6
+        assert (got[u, t:] == 1.0).all()
+
+
+def test_speech_processor_vs_reference_golden(fe, fixtures_pcm, ref_processor, tmp_path):
+    """SpeechProcessor drop-in through real wav files: filters, truncation, CMVN/SpecAugment order."""
+    import wave
+    from joeys2t_b200.speech_processor import SpeechProcessor
+    pcm, _ = fixtures_pcm
+    (tmp_path / "wav").mkdir()
+    for i, x in enumerate(pcm):
+        with wave.open(str(tmp_path / "wav" / f"c{i}.wav"), "wb") as w:
+            w.setnchannels(1)
+            w.setsampwidth(2)
+            w.setframerate(16000)
+            w.writeframes(x.tobytes())
+    g = ref_processor
+    sa = SA_CFGS["mustc"]
+    for vname, before in (("before", True), ("after", False)):
+        proc = SpeechProcessor(level="frame", num_freq=80, max_length=500, min_length=200,
+                               specaugment=sa, cmvn=dict(norm_means=True, norm_vars=True, before=before))
+        proc.root_path = tmp_path
+        for i in range(10):
+            for is_train in (True, False):
+                key = f"{vname}_{'train' if is_train else 'eval'}_c{i}"
+                np.random.seed(1000 + i)
+                y = proc(f"wav/c{i}.wav", is_train=is_train)
+                if int(g[key + "_none"]):
+                    assert y is None, key
+                    continue
+                assert list(y.shape) == g[key + "_shape"].tolist(), key
+                if key + "_full" in g.files:
+                    ref = g[key + "_full"]
+                    if before:
+                        cmvn_close(y, ref)
+                    else:
+                        # CMVN after SpecAugment: a masked column is constant, the reference divides
+                        # its own rounding noise by std = 1e-5 there (ill-conditioned)
+                        col_const = np.ptp(ref, axis=0) < 1e-2
+                        cmvn_close(y[:, ~col_const], ref[:, ~col_const])
+                        assert np.abs(y[:, col_const]).max(initial=0) < 0.2
+
+
+def test_truncation_before_cmvn(fe, fixtures_pcm, ref_fbank):
+    pcm, _ = fixtures_pcm
+    out, lens = fe.fbank_cmvn_specaug_ragged([pcm[2], pcm[4]], cmvn={}, max_frames=[500, 500])
+    assert lens.tolist() == [500, 500]
+    got = out.cpu().numpy()
+    cmvn_close(got[:500], O.cmvn(ref_fbank[2][:500]))
+    cmvn_close(got[500:], O.cmvn(ref_fbank[4][:500]))
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases
+# ------------------------------------------------------------------------------------------------
+def test_edge_lengths(fe):
+    rng = np.random.default_rng(0)
+    lens = [400, 401, 559, 560, 719, 720, 5359, 5360, 5361, 5519, 5520, 5521, 16000]
+    waves = [rng.integers(-20000, 20000, n).astype(np.int16) for n in lens]
+    out, nf = fe.fbank_cmvn_specaug_ragged(waves)
+    assert nf.tolist() == [O.num_frames(n) for n in lens]
+    got = out.cpu().numpy()
+    off = 0
+    for w, t in zip(waves, nf):
+        ref = O.extract_fbank_features(w)
+        assert np.abs(got[off:off + t] - ref).max() <= LOGMEL_ATOL
+        off += t
+
+
+def test_short_input_raises(fe):
+    from joeys2t_b200._lib import Js2tError
+    from joeys2t_b200.helpers_for_audio import extract_fbank_features
+    with pytest.raises(Js2tError):
+        fe.fbank_cmvn_specaug_ragged([np.zeros(399, np.int16)])
+    with pytest.raises(ValueError):  # quirk Q2: ValueError with or without output_path
+        extract_fbank_features(torch.zeros(1, 399), 16000)
+    with pytest.raises(ValueError):
+        extract_fbank_features(torch.zeros(1, 4000), 8000)
+
+
+def test_multichannel_takes_channel0(fe, fixtures_pcm):
+    pcm, _ = fixtures_pcm
+    x = pcm[0][:8000].astype(np.float32) / 32768.0
+    stereo = torch.from_numpy(np.stack([x, x[::-1].copy()]))
+    a, _ = fe.fbank_cmvn_specaug_ragged([stereo])
+    b, _ = fe.fbank_cmvn_specaug_ragged([x])
+    assert torch.equal(a, b)
+
+
+def test_extract_fbank_features_dropin(fe, fixtures_pcm, ref_fbank, tmp_path):
+    from joeys2t_b200.helpers_for_audio import extract_fbank_features, get_features
+    pcm, _ = fixtures_pcm
+    w = torch.from_numpy(pcm[5].astype(np.float32) / 32768.0).unsqueeze(0)
+    p = tmp_path / "f.npy"
+    feats = extract_fbank_features(w, 16000, output_path=p)
+    assert feats.dtype == np.float32 and feats.shape == ref_fbank[5].shape
+    assert np.abs(feats - ref_fbank[5]).max() <= LOGMEL_ATOL
+    assert p.is_file() and np.array_equal(np.load(p), feats)
+    # cache hit returns the stored array without recomputation
+    np.save(p, feats + 1)
+    assert np.array_equal(extract_fbank_features(w, 16000, output_path=p), feats + 1)
+    assert np.array_equal(get_features(tmp_path, "f.npy"), feats + 1)
+
+
+def test_gain_invariance_of_utterance_cmvn(fe, fixtures_pcm):
+    """Utterance CMVN output is independent of the input scale except through the floor
+    (scripts/gradio_demo.py:52-54 relies on it)."""
+    pcm, _ = fixtures_pcm
+    x = pcm[3]
+    a, _ = fe.fbank_cmvn_specaug_ragged([x], cmvn={})
+    b, _ = fe.fbank_cmvn_specaug_ragged([(x // 2 * 2).astype(np.int16)], cmvn={})
+    c, _ = fe.fbank_cmvn_specaug_ragged([((x // 2)).astype(np.int16)], cmvn={})
+    assert (b - c).abs().max().item() < 2e-3 and (a - b).abs().max().item() < 0.5
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic configs 2-4 at reduced size vs the oracle; full size through properties
+# ------------------------------------------------------------------------------------------------
+def test_librispeech_shaped_small_vs_oracle(fe):
+    from joeys2t_b200 import synthetic
+    waves = synthetic.librispeech_batch(6, seed=1234, lo=2.0, hi=4.0)
+    waves[2][5000:5000 + 4800] = 0  # exact digital silence: exercises the floor
+    out, nf = fe.fbank_cmvn_specaug_ragged(waves, cmvn={})
+    got = out.cpu().numpy()
+    off = 0
+    for w, t in zip(waves, nf):
+        raw = O.extract_fbank_features(w)
+        cmvn_close(got[off:off + t], O.cmvn_fp64(raw))
+        off += t
+
+
+def test_longform_mixed_dtype_vs_oracle(fe):
+    from joeys2t_b200 import synthetic
+    waves = synthetic.longform_batch(2, seed=3456)
+    waves = [w[:16000 * 31] for w in waves]
+    assert waves[0].dtype == np.int16 and waves[1].dtype == np.float32
+    out, nf = fe.fbank_cmvn_specaug_ragged(waves)
+    got = out.cpu().numpy()
+    off = 0
+    for w, t in zip(waves, nf):
+        ref = O.extract_fbank_features(w)
+        assert np.abs(got[off:off + t] - ref).max() <= LOGMEL_ATOL
+        off += t
+
+
+def test_full_size_properties(fe):
+    """Config-2 size (256 x 10-15 s): size-independent properties instead of the slow oracle."""
+    from joeys2t_b200 import synthetic
+    waves = synthetic.pooled_batch(256, seed=1234, lo=10.0, hi=15.0)
+    out, nf = fe.fbank_cmvn_specaug_ragged(waves, cmvn={})
+    assert int(nf.sum()) == sum(O.num_frames(len(w)) for w in waves)
+    assert torch.isfinite(out).all()
+    # per-utterance column means ~ 0 and stds ~ 1 after CMVN
+    off = 0
+    for t in nf[:32]:
+        blk = out[off:off + int(t)].double()
+        off += int(t)
+        assert blk.mean(0).abs().max().item() < 1e-4
+        assert (blk.std(0, unbiased=False) - 1).abs().max().item() < 1e-3
+    # batching must not change results: utterance 17 alone == utterance 17 in the batch
+    single, _ = fe.fbank_cmvn_specaug_ragged([waves[17]], cmvn={})
+    start = int(nf[:17].sum())
+    assert torch.equal(single, out[start:start + int(nf[17])])
+    # determinism
+    again, _ = fe.fbank_cmvn_specaug_ragged(waves, cmvn={})
+    assert torch.equal(again, out)
+    # spot-check a few utterances against the oracle
+    for u in (0, 100, 255):
+        start = int(nf[:u].sum())
+        cmvn_close(out[start:start + int(nf[u])].cpu().numpy(),
+                   O.cmvn_fp64(O.extract_fbank_features(waves[u])))
+
+
+# ------------------------------------------------------------------------------------------------
+# global CMVN (extension; oracle = reference CMVN formula on the frame-concatenation)
+# ------------------------------------------------------------------------------------------------
+def test_global_cmvn_two_pass(fe, fixtures_pcm, ref_fbank):
+    from joeys2t_b200 import distributed as D
+    pcm, _ = fixtures_pcm
+    packed = fe.PackedPCM(pcm)
+    plan = fe.Plan(packed.n_samples, packed.byte_off, packed.is_f32)
+    plan.set_cmvn("stats")
+    dev = packed.to_device()
+    raw = plan.execute(dev)
+    accum = D.new_accumulator("cuda")
+    plan.accumulate_global(accum)
+    s, q, n = O.global_cmvn_stats(ref_fbank)
+    a = accum.cpu().numpy()
+    assert a[160] == n
+    np.testing.assert_allclose(a[:80], s, rtol=2e-6)
+    np.testing.assert_allclose(a[80:160], q, rtol=2e-6)
+    # second pass: normalise in place with the finalised statistics
+    plan.set_cmvn("global")
+    plan.finalize_global(accum)
+    out = plan.normalize(raw).cpu().numpy()
+    want = np.concatenate(O.global_cmvn(ref_fbank), 0)
+    cmvn_close(out, want)
+    # single fused pass with the statistics known up front
+    mean, istd = D.stats_to_mean_istd(accum)
+    fused, _ = fe.fbank_cmvn_specaug_ragged(pcm, cmvn={}, global_stats=(mean, istd))
+    cmvn_close(fused.cpu().numpy(), want)
+    torch.cuda.synchronize()
+    plan.close()
