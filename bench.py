@@ -66,6 +66,19 @@ def workload_name(utts):
 # CPU leg: the oracle port on all host cores (the reference's own pattern is one process per core,
 # scripts/prepare_mustc.py:53,118 num_proc=16)
 # ----------------------------------------------------------------------------------------------
+_limits = None
+
+
+def _cpu_init():
+    """One thread per worker process (the BLAS behind numpy's matmul would otherwise oversubscribe)."""
+    global _limits
+    try:
+        from threadpoolctl import threadpool_limits
+        _limits = threadpool_limits(1)
+    except Exception:  # pylint: disable=broad-except
+        pass
+
+
 def _cpu_worker(w):
     from oracle import fbank_numpy as O
     return O.cmvn(O.extract_fbank_features(w)).shape[0]
@@ -78,7 +91,7 @@ def cpu_port_throughput(waves, cores, repeats=1):
     os.environ.setdefault("MKL_NUM_THREADS", "1")
     hours = sum(len(w) for w in waves) / SR / 3600.0
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
+    with ctx.Pool(cores, initializer=_cpu_init) as pool:
         pool.map(_cpu_worker, waves[:cores])  # warm the workers (imports, FFT plans)
         best = None
         for _ in range(repeats):
@@ -174,7 +187,7 @@ def run_reference(args):
     import multiprocessing as mp
     ctx = mp.get_context("fork")
     times = []
-    with ctx.Pool(cores) as pool:
+    with ctx.Pool(cores, initializer=_cpu_init) as pool:
         for _ in range(max(args.warmup, 1)):
             pool.map(_cpu_worker, sample[:cores])
         # keep the whole run within a few minutes

@@ -246,7 +246,19 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
     const int span = layout == JS2T_LAYOUT_PADDED ? p->pad_tmax : d.n_frames;
     d.out_row = row;
     row += span;
-    for (int f0 = 0; f0 < span; f0 += kTileFrames) tiles.push_back(TileDesc{u, f0});
+    for (int f0 = 0; f0 < span; f0 += kTileFrames) {
+      TileDesc t;
+      const long long per_frame = feat ? (long long)(kMel * sizeof(float))
+                                       : (long long)kHop * ((d.flags & 1) ? 4 : 2);
+      t.src_byte_off = d.pcm_byte_off + per_frame * f0;
+      t.out_row0 = d.out_row + f0;
+      t.utt = u;
+      t.frame0 = f0;
+      t.nf = d.n_frames - f0 < 0 ? 0 : (d.n_frames - f0 > kTileFrames ? kTileFrames : d.n_frames - f0);
+      t.rows = (short)(span - f0 > kTileFrames ? kTileFrames : span - f0);
+      t.flags = (short)(d.flags & 1);
+      tiles.push_back(t);
+    }
   }
   p->out_rows = row;
   p->n_tiles = (int)tiles.size();

@@ -12,10 +12,12 @@
 //   1. stage  the tile's PCM (int16 or fp32, 128-bit coalesced loads) into shared memory as the
 //             frame-independent pre-emphasised signal d[j] = x[j] - 0.97 x[j-1], plus 8-sample
 //             partial sums that give every frame's DC mean without re-reading the samples;
-//   2. fft    each half-warp transforms one frame: z[n] = y[2n] + i y[2n+1] (y = windowed frame,
-//             zero-padded to 512) as a 256-point complex FFT = radix-16 in registers, twiddle,
-//             16x16 transpose through shared memory, radix-16 in registers; the real-input split
-//             (partner bin 256-k fetched with warp shuffles) yields the power spectrum directly;
+//   2. fft    each half-warp transforms TWO frames at once with packed FP32x2 arithmetic (FADD2 /
+//             FMUL2 / FFMA2: one register pair = the same value of two frames): z[n] = y[2n] +
+//             i y[2n+1] (y = windowed frame, zero-padded to 512) as a 256-point complex FFT =
+//             radix-16 in registers, twiddle, 16x16 transpose through shared memory, radix-16 in
+//             registers; the real-input split (partner bin 256-k fetched with warp shuffles)
+//             yields the power spectrum directly;
 //   3. mel    lane = frame, warp = run of consecutive mel filters; the sparsity structure of the
 //             mel bank is compile-time (mel_structure.inc), the weights are __constant__ operands;
 //   4. store  log-mel tile to HBM with coalesced stores (+ per-tile column sums / sums of squares
@@ -36,74 +38,168 @@ constexpr int kWarps = kThreads / 32;
 constexpr float kPreemph = 0.97f;
 // (x_j - m) - 0.97f (x_{j-1} - m) == (x_j - 0.97f x_{j-1}) - (1 - 0.97f) m   (kaldi.py:183-198)
 constexpr float kDcScale = (float)(1.0 - (double)0.97f);
-constexpr float kLogFloor = 1.1920928955078125e-07f;  // FLT_EPSILON, kaldi.py:22,633
+constexpr float kLogFloor = 1.1920928955078125e-07f;      // FLT_EPSILON, kaldi.py:22,633
+constexpr float kLogOfFloor = -15.9423847198486328125f;   // float32 log(FLT_EPSILON) as torch computes it
+constexpr float kLn2 = 0.693147180559945309417f;
+
+// log(max(x, eps)) (kaldi.py:633).  Floored cells (digital silence) get the exact float32 value the
+// reference produces, so they are bit-identical; elsewhere lg2.approx * ln2 is within ~1e-6 absolute.
+// The argument is >= eps, never denormal, so the .ftz form needs no range fix-up.
+__device__ __forceinline__ float log_floor(float x) {
+  float l;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fmaxf(x, kLogFloor)));
+  return x > kLogFloor ? l * kLn2 : kLogOfFloor;
+}
 
 // ---- shared memory carve-up (bytes) -------------------------------------------------------------
-constexpr int kDFloats = 5376;                   // >= kTileSamples (5360), multiple of 8
-constexpr int kPsumFloats = kDFloats / 8;        // 672 partial sums of 8 samples
-constexpr int kExchStride = 17;                  // float2 per row of the 16x16 transpose (padded)
-constexpr int kExchPerWarp = 2 * 16 * kExchStride;  // float2: two half-warps
-constexpr int kPStride = 33;                     // P[k][frame], padded: conflict-free both ways
+constexpr int kDFloats = 5376;                    // >= kTileSamples (5360) + 16 zeroed tail floats
+constexpr int kPsumFloats = kDFloats / 8;         // 672 partial sums of 8 samples
+constexpr int kExchStride = 17;                   // 8-byte words per row of the 16x16 transpose (padded)
+constexpr int kExchPerWarp = 2 * 16 * kExchStride;   // 8-byte words: two half-warps
+constexpr int kPStride = 34;                      // P[k][frame]: even (64-bit stores), 2k+f banks
 constexpr int kPFloats = 257 * kPStride;
-constexpr int kOutStride = 81;                   // outTile[frame][mel], padded
+constexpr int kOutStride = 81;                    // outTile[frame][mel], padded
 constexpr int kOutFloats = kTileFrames * kOutStride;
 
 constexpr int kOffD = 0;
 constexpr int kOffPsum = kOffD + kDFloats * 4;
 constexpr int kOffMean = kOffPsum + kPsumFloats * 4;
 constexpr int kOffWin = kOffMean + kTileFrames * 4;
-constexpr int kOffTw256 = kOffWin + kFrameLen * 4;
+constexpr int kOffTw256 = kOffWin + (kFrameLen + 16) * 4;
 constexpr int kOffTw512 = kOffTw256 + 256 * 8;
 constexpr int kOffExch = kOffTw512 + 136 * 8;
 constexpr int kOffP = kOffExch + kWarps * kExchPerWarp * 8;
-constexpr int kSmemBytes = kOffP + kPFloats * 4;
+constexpr int kOffRaw = (kOffP + kPFloats * 4 + 15) / 16 * 16;  // 16 B lead-in + int16 PCM of one tile (TMA target)
+constexpr int kRawBytes = 16 + kTileSamples * 2;
+constexpr int kOffBar = kOffRaw + ((kRawBytes + 15) / 16) * 16;
+constexpr int kSmemBytes = kOffBar + 16;
 static_assert(kOutFloats * 4 <= kWarps * kExchPerWarp * 8, "out tile aliases the exchange buffers");
-static_assert(kOffExch % 16 == 0 && kOffP % 16 == 0 && kOffTw256 % 16 == 0, "alignment");
+static_assert(kWarps * kStatsPerTile * 4 <= kDFloats * 4, "per-warp statistics alias the d buffer");
+static_assert(kOffExch % 16 == 0 && kOffP % 16 == 0 && kOffTw256 % 16 == 0 && kOffWin % 16 == 0 &&
+                  kOffRaw % 16 == 0 && kOffBar % 8 == 0,
+              "alignment");
+static_assert(2 * (kSmemBytes + 1024) <= 227 * 1024, "two CTAs per SM");
 
 int fbank_smem_bytes() { return kSmemBytes; }
 
-// ---- small complex helpers -----------------------------------------------------------------------
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 w) {
-  return make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+// ---- packed FP32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2) ----------------------------------
+// One 64-bit register pair holds the same quantity for two different frames (lo = frame A,
+// hi = frame B).  The FP32 pipe rate per lane is unchanged, but one issue slot now carries two
+// frames' worth of butterfly arithmetic, which frees issue slots for the LDS/STS/SHFL traffic
+// (tools/microbench_fp32x2.cu: FFMA 120, FFMA2 125 lane-ops/clk/SM; with 2 LDS per 8 FMAs 61 -> 77).
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ u64 bc(float s) { return pk(s, s); }  // broadcast (folds into a .F32 operand)
+__device__ __forceinline__ void upk(u64 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+  u64 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+// complex number of two frames: re = (re_A, re_B), im = (im_A, im_B)
+struct C2 {
+  u64 re, im;
+};
+__device__ __forceinline__ C2 cadd(C2 a, C2 b) { return C2{add2(a.re, b.re), add2(a.im, b.im)}; }
+__device__ __forceinline__ C2 csub(C2 a, C2 b) { return C2{sub2(a.re, b.re), sub2(a.im, b.im)}; }
+// a * (wr + i wi) with scalar (frame-independent) twiddle
+__device__ __forceinline__ C2 cmul(C2 a, float wr, float wi) {
+  const u64 r = fma2(a.im, bc(-wi), mul2(a.re, bc(wr)));
+  const u64 i = fma2(a.im, bc(wr), mul2(a.re, bc(wi)));
+  return C2{r, i};
 }
 // a + (-i) b  and  a + (+i) b
-__device__ __forceinline__ float2 add_mi(float2 a, float2 b) { return make_float2(a.x + b.y, a.y - b.x); }
-__device__ __forceinline__ float2 add_pi(float2 a, float2 b) { return make_float2(a.x - b.y, a.y + b.x); }
+__device__ __forceinline__ C2 add_mi(C2 a, C2 b) { return C2{add2(a.re, b.im), sub2(a.im, b.re)}; }
+__device__ __forceinline__ C2 add_pi(C2 a, C2 b) { return C2{sub2(a.re, b.im), add2(a.im, b.re)}; }
 
 #define JS2T_R4(a0, a1, a2, a3, b0, b1, b2, b3) \
   {                                             \
-    const float2 t0 = cadd(a0, a2);             \
-    const float2 t1 = csub(a0, a2);             \
-    const float2 t2 = cadd(a1, a3);             \
-    const float2 t3 = csub(a1, a3);             \
+    const C2 t0 = cadd(a0, a2);                 \
+    const C2 t1 = csub(a0, a2);                 \
+    const C2 t2 = cadd(a1, a3);                 \
+    const C2 t3 = csub(a1, a3);                 \
     b0 = cadd(t0, t2);                          \
     b2 = csub(t0, t2);                          \
     b1 = add_mi(t1, t3);                        \
     b3 = add_pi(t1, t3);                        \
   }
+// same with a3 == 0 (zero-padded tail of the 400-sample frame)
+#define JS2T_R4_Z3(a0, a1, a2, b0, b1, b2, b3) \
+  {                                            \
+    const C2 t0 = cadd(a0, a2);                \
+    const C2 t1 = csub(a0, a2);                \
+    b0 = cadd(t0, a1);                         \
+    b2 = csub(t0, a1);                         \
+    b1 = add_mi(t1, a1);                       \
+    b3 = add_pi(t1, a1);                       \
+  }
 
-// 16-point complex FFT in registers, natural order in and out (4 x 4 Cooley-Tukey).
-__device__ __forceinline__ void fft16(float2 (&v)[16]) {
+// 16-point complex FFT in registers, natural order in and out (4 x 4 Cooley-Tukey), on two frames
+// at once.  kZeroTail: inputs 13, 14, 15 are known to be zero (first pass: samples >= 416 of the
+// 512-point frame), which removes their additions.
+template <bool kZeroTail>
+__device__ __forceinline__ void fft16(C2 (&v)[16]) {
   constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
+  {
+    C2 b0, b1, b2, b3;
+    JS2T_R4(v[0], v[4], v[8], v[12], b0, b1, b2, b3);
+    v[0] = b0; v[4] = b1; v[8] = b2; v[12] = b3;
+  }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 b0, b1, b2, b3;
-    JS2T_R4(v[i], v[i + 4], v[i + 8], v[i + 12], b0, b1, b2, b3);
+  for (int i = 1; i < 4; ++i) {
+    C2 b0, b1, b2, b3;
+    if (kZeroTail) {
+      JS2T_R4_Z3(v[i], v[i + 4], v[i + 8], b0, b1, b2, b3);
+    } else {
+      JS2T_R4(v[i], v[i + 4], v[i + 8], v[i + 12], b0, b1, b2, b3);
+    }
     v[i] = b0; v[i + 4] = b1; v[i + 8] = b2; v[i + 12] = b3;
   }
   // twiddles W16^(i*q) on v[i + 4q]
-  v[5] = cmul(v[5], make_float2(c1, -s1));                        // W^1
-  v[9] = make_float2((v[9].x + v[9].y) * h, (v[9].y - v[9].x) * h);      // W^2 = (1 - i)/sqrt2
-  v[13] = cmul(v[13], make_float2(s1, -c1));                      // W^3
-  v[6] = make_float2((v[6].x + v[6].y) * h, (v[6].y - v[6].x) * h);      // W^2
-  v[10] = make_float2(v[10].y, -v[10].x);                         // W^4 = -i
-  v[14] = make_float2((v[14].y - v[14].x) * h, -(v[14].x + v[14].y) * h);  // W^6 = (-1 - i)/sqrt2
-  v[7] = cmul(v[7], make_float2(s1, -c1));                        // W^3
-  v[11] = make_float2((v[11].y - v[11].x) * h, -(v[11].x + v[11].y) * h);  // W^6
-  v[15] = cmul(v[15], make_float2(-c1, s1));                      // W^9
-  float2 o[16];
+  v[5] = cmul(v[5], c1, -s1);   // W^1
+  v[13] = cmul(v[13], s1, -c1); // W^3
+  v[7] = cmul(v[7], s1, -c1);   // W^3
+  v[15] = cmul(v[15], -c1, s1); // W^9
+  {                             // W^2 = (1 - i)/sqrt2 : (x + y, y - x) * h
+    const u64 hh = bc(h);
+    C2 t = v[9];
+    v[9] = C2{mul2(add2(t.re, t.im), hh), mul2(sub2(t.im, t.re), hh)};
+    t = v[6];
+    v[6] = C2{mul2(add2(t.re, t.im), hh), mul2(sub2(t.im, t.re), hh)};
+    // W^6 = (-1 - i)/sqrt2 : (y - x, -(x + y)) * h
+    const u64 nh = bc(-h);
+    t = v[14];
+    v[14] = C2{mul2(sub2(t.im, t.re), hh), mul2(add2(t.re, t.im), nh)};
+    t = v[11];
+    v[11] = C2{mul2(sub2(t.im, t.re), hh), mul2(add2(t.re, t.im), nh)};
+  }
+  {  // W^4 = -i : (y, -x); the negation is folded into the consumers below via a swapped butterfly
+    const C2 t = v[10];
+    v[10] = C2{t.im, sub2(0ull, t.re)};
+  }
+  C2 o[16];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     JS2T_R4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3], o[q], o[q + 4], o[q + 8], o[q + 12]);
@@ -121,11 +217,6 @@ __device__ __forceinline__ int4 ldg_stream_int4(const void* p) {
   return r;
 }
 
-__device__ __forceinline__ float pcm_sample(const uint8_t* base, long long idx, bool is_f32) {
-  return is_f32 ? __ldg(reinterpret_cast<const float*>(base) + idx) * 32768.0f
-                : (float)__ldg(reinterpret_cast<const short*>(base) + idx);
-}
-
 // ---- mel stage: one run of consecutive filters [M0, M1), lane = frame ---------------------------------
 template <int M0, int M1>
 __device__ __forceinline__ void mel_group(const float* __restrict__ Pl, float* __restrict__ orow) {
@@ -137,7 +228,7 @@ __device__ __forceinline__ void mel_group(const float* __restrict__ Pl, float* _
       if constexpr ((s) < M1) hi_acc = fmaf(c_mel_wu[k], p, hi_acc);                 \
       if constexpr ((s) > M0) lo_acc = fmaf(c_mel_wd[k], p, lo_acc);                 \
     }                                                                                \
-    if constexpr ((s) > M0) orow[(s)-1] = __logf(fmaxf(lo_acc, kLogFloor));          \
+    if constexpr ((s) > M0) orow[(s)-1] = log_floor(lo_acc);                         \
     lo_acc = hi_acc;                                                                 \
     hi_acc = 0.f;                                                                    \
   }
@@ -146,8 +237,51 @@ __device__ __forceinline__ void mel_group(const float* __restrict__ Pl, float* _
 }
 
 // =====================================================================================================
-//  Kernel A: PCM tile -> log-mel tile (+ statistics | normalisation)
+//  Kernel A: PCM tiles -> log-mel tiles (+ statistics | normalisation).  Persistent: every CTA walks
+//  tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the int16 PCM of the *next* tile is fetched by one
+//  bulk async copy (cp.async.bulk, TMA 1-D) into shared memory while the current tile is computed.
 // =====================================================================================================
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// one thread: arm the barrier with the byte count and start the bulk copy global -> shared
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// bytes of int16 PCM staged for a tile: 16 bytes of lead-in (the 8 samples before the tile, when
+// the tile is not at the start of the utterance) + the tile's samples
+__device__ __forceinline__ void prefetch_tile(const FbankLaunch& p, const TileDesc& t, unsigned char* sRaw,
+                                              unsigned long long* bar) {
+  const unsigned lead = t.frame0 > 0 ? 16u : 0u;
+  const unsigned bytes = (unsigned)(((t.nf - 1) * kHop + kFrameLen) * 2) + lead;
+  tma_load_1d(sRaw + 16 - lead, p.pcm + t.src_byte_off - lead, bytes, bar);
+}
+
 __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaunch p) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* sD = reinterpret_cast<float*>(smem + kOffD);
@@ -156,228 +290,314 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
   float* sWin = reinterpret_cast<float*>(smem + kOffWin);
   float2* sTw256 = reinterpret_cast<float2*>(smem + kOffTw256);
   float2* sTw512 = reinterpret_cast<float2*>(smem + kOffTw512);
-  float2* sExch = reinterpret_cast<float2*>(smem + kOffExch);
+  u64* sExch = reinterpret_cast<u64*>(smem + kOffExch);
   float* sOut = reinterpret_cast<float*>(smem + kOffExch);  // aliases sExch after the FFT phase
+  float* sStat = reinterpret_cast<float*>(smem + kOffD);    // aliases sD after the FFT phase
   float* sP = reinterpret_cast<float*>(smem + kOffP);
+  unsigned char* sRaw = smem + kOffRaw;
+  unsigned long long* sBar = reinterpret_cast<unsigned long long*>(smem + kOffBar);
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
 
-  const TileDesc td = p.tiles[blockIdx.x];
-  const UttDesc ud = p.utts[td.utt];
-  const int frame0 = td.frame0;
-  const int nf = max(0, min(kTileFrames, ud.n_frames - frame0));  // valid frames in this tile
-  // rows this tile owns in the output (padded layout: up to Tmax, the tail is padding)
-  const int rows = p.pad_tmax > 0 ? min(kTileFrames, p.pad_tmax - frame0) : nf;
-  float* __restrict__ out_tile = p.out + (ud.out_row + frame0) * (long long)kMel;
-
-  if (nf == 0) {  // pure padding tile
-    if (p.tile_stats != nullptr && tid < kStatsPerTile)
-      p.tile_stats[(long long)blockIdx.x * kStatsPerTile + tid] = 0.f;
-    for (int e = tid; e < rows * kMel; e += kThreads) out_tile[e] = p.pad_value;
-    return;
-  }
-
-  // ---- phase 0: tables into shared memory ---------------------------------------------------------
-  for (int i = tid; i < kFrameLen; i += kThreads) sWin[i] = p.tab.window_half[i];
+  // ---- once per CTA: tables into shared memory, barrier init ------------------------------------------
+  for (int i = tid; i < kFrameLen + 16; i += kThreads) sWin[i] = i < kFrameLen ? p.tab.window_half[i] : 0.f;
   sTw256[tid] = p.tab.tw256[tid];
   if (tid < 136) sTw512[tid] = p.tab.tw512[tid];
+  if (tid == 0) mbar_init(sBar, 1);
+  __syncthreads();
 
-  // ---- phase 1: stage PCM as d[j] = x[j] - 0.97 x[j-1] and 8-sample partial sums ------------------
-  {
-    const bool is_f32 = (ud.flags & 1) != 0;
-    const uint8_t* base = p.pcm + ud.pcm_byte_off;
-    const long long s0 = (long long)frame0 * kHop;  // first sample of the tile
-    const int n_chunks = ((nf - 1) * kHop + kFrameLen) >> 3;
-    for (int c = tid; c < n_chunks; c += kThreads) {
-      const long long j0 = s0 + 8ll * c;
-      float x[8];
-      if (is_f32) {
-        const int4 a = ldg_stream_int4(reinterpret_cast<const float*>(base) + j0);
-        const int4 b = ldg_stream_int4(reinterpret_cast<const float*>(base) + j0 + 4);
-        x[0] = __int_as_float(a.x) * 32768.f; x[1] = __int_as_float(a.y) * 32768.f;
-        x[2] = __int_as_float(a.z) * 32768.f; x[3] = __int_as_float(a.w) * 32768.f;
-        x[4] = __int_as_float(b.x) * 32768.f; x[5] = __int_as_float(b.y) * 32768.f;
-        x[6] = __int_as_float(b.z) * 32768.f; x[7] = __int_as_float(b.w) * 32768.f;
+  int tile = blockIdx.x;
+  const int G = gridDim.x;
+  TileDesc cur = p.tiles[tile];  // grid <= n_tiles
+  unsigned parity = 0;
+  if (tid == 0 && cur.nf > 0 && !(cur.flags & 1)) prefetch_tile(p, cur, sRaw, sBar);
+
+  while (true) {
+    const int next_tile = tile + G;
+    const bool has_next = next_tile < p.n_tiles;
+    TileDesc nxt = cur;
+    if (has_next) nxt = p.tiles[next_tile];  // consumed one iteration later: latency hidden
+    const bool next_tma = has_next && nxt.nf > 0 && !(nxt.flags & 1);
+
+    const int nf = cur.nf;      // valid frames in this tile
+    const int rows = cur.rows;  // rows owned in the output (padded layout: the tail is padding)
+    float* __restrict__ out_tile = p.out + cur.out_row0 * (long long)kMel;
+
+    if (nf == 0) {  // pure padding tile
+      if (p.tile_stats != nullptr && tid < kStatsPerTile)
+        p.tile_stats[(long long)tile * kStatsPerTile + tid] = 0.f;
+      for (int e = tid; e < rows * kMel; e += kThreads) out_tile[e] = p.pad_value;
+      if (tid == 0 && next_tma) prefetch_tile(p, nxt, sRaw, sBar);
+    } else {
+      // ---- phase 1: stage PCM as d[j] = x[j] - 0.97 x[j-1] and 8-sample partial sums ----------------
+      const int n_chunks = 20 * nf + 30;  // ((nf - 1) * 160 + 400) / 8
+      if (tid < 16) sD[8 * n_chunks + tid] = 0.f;  // the 16 floats past the tile that frame loads may touch
+      if (!(cur.flags & 1)) {
+        // int16 PCM, already in shared memory (bulk async copy issued one tile ago)
+        mbar_wait(sBar, parity);
+        parity ^= 1u;
+        const int4* raw4 = reinterpret_cast<const int4*>(sRaw + 16);
+        const short* raw = reinterpret_cast<const short*>(sRaw + 16);
+        const bool at_start = cur.frame0 == 0;
+#pragma unroll 1
+        for (int c = tid; c < n_chunks; c += kThreads) {
+          const int4 a = raw4[c];
+          // previous sample; at the very first sample of the utterance any finite value will do (it
+          // only reaches frame position 0, where the povey window is exactly 0)
+          const int prev = (c == 0 && at_start) ? (int)raw[0] : (int)raw[8 * c - 1];
+          float x[8];
+          x[0] = (float)((a.x << 16) >> 16); x[1] = (float)(a.x >> 16);
+          x[2] = (float)((a.y << 16) >> 16); x[3] = (float)(a.y >> 16);
+          x[4] = (float)((a.z << 16) >> 16); x[5] = (float)(a.z >> 16);
+          x[6] = (float)((a.w << 16) >> 16); x[7] = (float)(a.w >> 16);
+          const float xm1 = (float)prev;
+          float4 d0, d1;
+          d0.x = fmaf(-kPreemph, xm1, x[0]);
+          d0.y = fmaf(-kPreemph, x[0], x[1]);
+          d0.z = fmaf(-kPreemph, x[1], x[2]);
+          d0.w = fmaf(-kPreemph, x[2], x[3]);
+          d1.x = fmaf(-kPreemph, x[3], x[4]);
+          d1.y = fmaf(-kPreemph, x[4], x[5]);
+          d1.z = fmaf(-kPreemph, x[5], x[6]);
+          d1.w = fmaf(-kPreemph, x[6], x[7]);
+          reinterpret_cast<float4*>(sD)[2 * c] = d0;
+          reinterpret_cast<float4*>(sD)[2 * c + 1] = d1;
+          sPsum[c] = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+        }
       } else {
-        const int4 a = ldg_stream_int4(reinterpret_cast<const short*>(base) + j0);
-        x[0] = (float)(short)(a.x & 0xffff); x[1] = (float)(a.x >> 16);
-        x[2] = (float)(short)(a.y & 0xffff); x[3] = (float)(a.y >> 16);
-        x[4] = (float)(short)(a.z & 0xffff); x[5] = (float)(a.z >> 16);
-        x[6] = (float)(short)(a.w & 0xffff); x[7] = (float)(a.w >> 16);
+        // float32 PCM in [-1, 1): straight from global memory (no staging buffer of that size)
+        const float* src = reinterpret_cast<const float*>(p.pcm + cur.src_byte_off);
+        const bool at_start = cur.frame0 == 0;
+#pragma unroll 1
+        for (int c = tid; c < n_chunks; c += kThreads) {
+          const int4 a = ldg_stream_int4(src + 8 * c);
+          const int4 b = ldg_stream_int4(src + 8 * c + 4);
+          float x[8];
+          x[0] = __int_as_float(a.x) * 32768.f; x[1] = __int_as_float(a.y) * 32768.f;
+          x[2] = __int_as_float(a.z) * 32768.f; x[3] = __int_as_float(a.w) * 32768.f;
+          x[4] = __int_as_float(b.x) * 32768.f; x[5] = __int_as_float(b.y) * 32768.f;
+          x[6] = __int_as_float(b.z) * 32768.f; x[7] = __int_as_float(b.w) * 32768.f;
+          const float xm1 = (c == 0 && at_start) ? x[0] : __ldg(src + 8 * c - 1) * 32768.f;
+          float4 d0, d1;
+          d0.x = fmaf(-kPreemph, xm1, x[0]);
+          d0.y = fmaf(-kPreemph, x[0], x[1]);
+          d0.z = fmaf(-kPreemph, x[1], x[2]);
+          d0.w = fmaf(-kPreemph, x[2], x[3]);
+          d1.x = fmaf(-kPreemph, x[3], x[4]);
+          d1.y = fmaf(-kPreemph, x[4], x[5]);
+          d1.z = fmaf(-kPreemph, x[5], x[6]);
+          d1.w = fmaf(-kPreemph, x[6], x[7]);
+          reinterpret_cast<float4*>(sD)[2 * c] = d0;
+          reinterpret_cast<float4*>(sD)[2 * c + 1] = d1;
+          sPsum[c] = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+        }
       }
-      // previous sample; at the very first sample of the utterance any finite value will do
-      // (it only reaches frame position 0, where the povey window is exactly 0)
-      const float xm1 = (j0 > 0) ? pcm_sample(base, j0 - 1, is_f32) : x[0];
-      float4 d0, d1;
-      d0.x = fmaf(-kPreemph, xm1, x[0]);
-      d0.y = fmaf(-kPreemph, x[0], x[1]);
-      d0.z = fmaf(-kPreemph, x[1], x[2]);
-      d0.w = fmaf(-kPreemph, x[2], x[3]);
-      d1.x = fmaf(-kPreemph, x[3], x[4]);
-      d1.y = fmaf(-kPreemph, x[4], x[5]);
-      d1.z = fmaf(-kPreemph, x[5], x[6]);
-      d1.w = fmaf(-kPreemph, x[6], x[7]);
-      reinterpret_cast<float4*>(sD)[2 * c] = d0;
-      reinterpret_cast<float4*>(sD)[2 * c + 1] = d1;
-      sPsum[c] = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
-    }
-  }
-  __syncthreads();
+      __syncthreads();
+      // the staging buffer is free again: start fetching the next tile's PCM behind the compute below
+      if (tid == 0 && next_tma) prefetch_tile(p, nxt, sRaw, sBar);
 
-  // per-frame DC mean (kaldi.py:183-186), pre-multiplied by (1 - 0.97): 8 threads per frame
-  {
-    const int f = tid >> 3, sub = tid & 7;
-    float s = 0.f;
-    if (f < nf) {
-      const float* ps = sPsum + 20 * f;
-#pragma unroll
-      for (int i = 0; i < 7; ++i) {
-        const int c = sub + 8 * i;
-        if (c < 50) s += ps[c];
-      }
-    }
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    if (sub == 0) sMean[f] = (s / 400.0f) * kDcScale;
-  }
-  __syncthreads();
-
-  // ---- phase 2: one frame per half-warp -> power spectrum P[k][frame] -----------------------------
-  {
-    const int half = lane >> 4;
-    const int r = lane & 15;
-    float2* exch = sExch + warp * kExchPerWarp + half * (16 * kExchStride);
-    const int partner = (lane & 16) | ((16 - r) & 15);
-    for (int it = warp; it < 16; it += kWarps) {
-      if (it >= nf) break;  // both frames of this iteration are past the end (warp-uniform)
-      const int f = it + 16 * half;
-      const bool valid = f < nf;
-      float2 v[16];
+      // per-frame DC mean (kaldi.py:183-186), pre-multiplied by (1 - 0.97): 8 threads per frame
       {
-        const float mc = sMean[valid ? f : 0];
-        const float* dfr = sD + (valid ? f : 0) * kHop + 2 * r;
-        const float* wfr = sWin + 2 * r;
+        const int f = tid >> 3, sub = tid & 7;
+        float s = 0.f;
+        if (f < nf) {
+          const float* ps = sPsum + 20 * f + sub;
 #pragma unroll
-        for (int n1 = 0; n1 < 12; ++n1) {
-          const float2 x = *reinterpret_cast<const float2*>(dfr + 32 * n1);
-          const float2 w = *reinterpret_cast<const float2*>(wfr + 32 * n1);
-          v[n1] = make_float2((x.x - mc) * w.x, (x.y - mc) * w.y);
+          for (int i = 0; i < 6; ++i) s += ps[8 * i];
+          if (sub < 2) s += ps[48];
         }
-        if (r < 8) {  // samples 384 + 2r, 385 + 2r < 400
-          const float2 x = *reinterpret_cast<const float2*>(dfr + 384);
-          const float2 w = *reinterpret_cast<const float2*>(wfr + 384);
-          v[12] = make_float2((x.x - mc) * w.x, (x.y - mc) * w.y);
-        } else {
-          v[12] = make_float2(0.f, 0.f);
-        }
-        v[13] = v[14] = v[15] = make_float2(0.f, 0.f);
-        if (!valid) {
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (sub == 0) sMean[f] = (s / 400.0f) * kDcScale;
+      }
+      __syncthreads();
+
+      // ---- phase 2: two frames per half-warp (packed), four per warp -> power spectrum P[k][frame] ----
+      if (4 * warp < nf) {
+        const int half = lane >> 4;
+        const int r = lane & 15;
+        u64* exch = sExch + warp * kExchPerWarp + half * (16 * kExchStride);
+        const int partner = (lane & 16) | ((16 - r) & 15);
+        const int fA = 4 * warp + 2 * half;  // frames fA, fA + 1 (even: 64-bit P stores)
+        const int lA = min(fA, nf - 1), lB = min(fA + 1, nf - 1);  // past-the-end frames redo the last one
+        C2 v[16];
+        {
+          const u64 mc = pk(sMean[lA], sMean[lB]);
+          const float* dA = sD + lA * kHop + 2 * r;
+          const float* dB = sD + lB * kHop + 2 * r;
+          const float* wfr = sWin + 2 * r;
 #pragma unroll
-          for (int i = 0; i < 13; ++i) v[i] = make_float2(0.f, 0.f);
+          for (int n1 = 0; n1 < 13; ++n1) {  // n1 == 12: lanes r >= 8 read the zeroed window tail
+            const float2 a = *reinterpret_cast<const float2*>(dA + 32 * n1);
+            const float2 b = *reinterpret_cast<const float2*>(dB + 32 * n1);
+            const float2 w = *reinterpret_cast<const float2*>(wfr + 32 * n1);
+            v[n1].re = mul2(sub2(pk(a.x, b.x), mc), bc(w.x));
+            v[n1].im = mul2(sub2(pk(a.y, b.y), mc), bc(w.y));
+          }
+          v[13] = v[14] = v[15] = C2{0ull, 0ull};
+        }
+        // pass 1: DFT over n1 (lane = n2 = r), then twiddle by W_256^(n2*k1)
+        fft16<true>(v);
+#pragma unroll
+        for (int k1 = 1; k1 < 16; ++k1) {
+          const float2 w = sTw256[k1 * 16 + r];
+          v[k1] = cmul(v[k1], w.x, w.y);
+        }
+        // 16x16 transpose inside the half-warp, real parts then imaginary parts (keeps registers flat)
+        __syncwarp();
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) exch[k1 * kExchStride + r] = v[k1].re;
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 16; ++n2) v[n2].re = exch[r * kExchStride + n2];
+        __syncwarp();
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) exch[k1 * kExchStride + r] = v[k1].im;
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 16; ++n2) v[n2].im = exch[r * kExchStride + n2];
+        // pass 2: DFT over n2 (lane = k1 = r): v[k2] = Z[r + 16 k2]
+        fft16<false>(v);
+
+        // real-input split: bins k = r + 16 j and 256 - k from Z[k] and Z[256 - k] (partner lane)
+        float* Pf = sP + fA;
+        const bool r0 = (r == 0);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          // partner register index: 15 - j, except in lane r == 0 where it is (16 - j) & 15
+          const C2 ma = v[(15 - j) & 15];
+          const C2 mb = v[(16 - j) & 15];
+          float s0, s1, s2, s3, t0, t1, t2, t3;
+          upk(ma.re, s0, s1); upk(ma.im, s2, s3);
+          upk(mb.re, t0, t1); upk(mb.im, t2, t3);
+          const float q0 = __shfl_sync(0xffffffffu, r0 ? t0 : s0, partner);
+          const float q1 = __shfl_sync(0xffffffffu, r0 ? t1 : s1, partner);
+          const float q2 = __shfl_sync(0xffffffffu, r0 ? t2 : s2, partner);
+          const float q3 = __shfl_sync(0xffffffffu, r0 ? t3 : s3, partner);
+          if (j == 8 && !r0) continue;  // k = 128 exists only in lane r == 0
+          const C2 z = v[j];
+          const C2 zp = C2{pk(q0, q1), pk(q2, q3)};
+          const int k = r + 16 * j;
+          const float2 w = sTw512[k];
+          const u64 er = add2(z.re, zp.re), ei = sub2(z.im, zp.im);
+          const u64 orr = add2(z.im, zp.im), oi = sub2(zp.re, z.re);
+          const u64 tr = fma2(oi, bc(-w.y), mul2(orr, bc(w.x)));
+          const u64 ti = fma2(orr, bc(w.y), mul2(oi, bc(w.x)));
+          const u64 ar = add2(er, tr), ai = add2(ei, ti);
+          const u64 br = sub2(er, tr), bi = sub2(ei, ti);
+          *reinterpret_cast<u64*>(Pf + k * kPStride) = fma2(ar, ar, mul2(ai, ai));
+          *reinterpret_cast<u64*>(Pf + (256 - k) * kPStride) = fma2(br, br, mul2(bi, bi));
         }
       }
-      // pass 1: DFT over n1 (lane = n2 = r), then twiddle by W_256^(n2*k1)
-      fft16(v);
-#pragma unroll
-      for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], sTw256[k1 * 16 + r]);
-      // 16x16 transpose inside the half-warp
-      __syncwarp();
-#pragma unroll
-      for (int k1 = 0; k1 < 16; ++k1) exch[k1 * kExchStride + r] = v[k1];
-      __syncwarp();
-#pragma unroll
-      for (int n2 = 0; n2 < 16; ++n2) v[n2] = exch[r * kExchStride + n2];
-      // pass 2: DFT over n2 (lane = k1 = r): v[k2] = Z[r + 16 k2]
-      fft16(v);
+      __syncthreads();
 
-      // real-input split: bins k = r + 16 j and 256 - k from Z[k] and Z[256 - k] (partner lane)
-      float* Pf = sP + f;
-#pragma unroll
-      for (int j = 0; j < 9; ++j) {
-        // partner register index: 15 - j, except in lane r == 0 where it is (16 - j) & 15
-        const float2 mine_a = v[(15 - j) & 15];
-        const float2 mine_b = v[(16 - j) & 15];
-        const float2 send = (r == 0) ? mine_b : mine_a;
-        float2 zp;
-        zp.x = __shfl_sync(0xffffffffu, send.x, partner);
-        zp.y = __shfl_sync(0xffffffffu, send.y, partner);
-        if (j == 8 && r != 0) continue;  // k = 128 exists only in lane r == 0
-        const float2 z = v[j];
-        const int k = r + 16 * j;
-        const float2 w = sTw512[k];
-        const float er = z.x + zp.x, ei = z.y - zp.y;
-        const float orr = z.y + zp.y, oi = zp.x - z.x;
-        const float tr = fmaf(w.x, orr, -w.y * oi);
-        const float ti = fmaf(w.x, oi, w.y * orr);
-        const float ar = er + tr, ai = ei + ti;
-        const float br = er - tr, bi = ei - ti;
-        if (valid) {
-          Pf[k * kPStride] = fmaf(ar, ar, ai * ai);
-          Pf[(256 - k) * kPStride] = fmaf(br, br, bi * bi);
-        }
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 3: mel filterbank + log, lane = frame, warp = run of filters --------------------------
-  {
-    const float* Pl = sP + lane;
-    float* orow = sOut + lane * kOutStride;
-    if (lane < nf) {
-      switch (warp) {
+      // ---- phase 3: mel filterbank + log, lane = frame, warp = run of filters -------------------------
+      {
+        const float* Pl = sP + lane;
+        float* orow = sOut + lane * kOutStride;
+        if (lane < nf) {
+          switch (warp) {
 #define JS2T_GRP(g, m0, m1) \
   case g:                   \
     mel_group<m0, m1>(Pl, orow); \
     break;
-        JS2T_MEL_GROUPS(JS2T_GRP)
+            JS2T_MEL_GROUPS(JS2T_GRP)
 #undef JS2T_GRP
-        default:
-          break;
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 4: store -----------------------------------------------------------------------------
-  if (p.epilogue == kEpiRaw) {
-    for (int e = tid; e < rows * kMel; e += kThreads) {
-      const int f = e / kMel, m = e - f * kMel;
-      out_tile[e] = (f < nf) ? sOut[f * kOutStride + m] : p.pad_value;
-    }
-    if (p.tile_stats != nullptr && tid < kStatsPerTile) {
-      // column sum (tid < 80) or sum of squares (tid >= 80) over the tile's valid frames
-      const int m = tid < kMel ? tid : tid - kMel;
-      const bool sq = tid >= kMel;
-      float acc = 0.f;
-      for (int f = 0; f < nf; ++f) {
-        const float x = sOut[f * kOutStride + m];
-        acc += sq ? x * x : x;
-      }
-      p.tile_stats[(long long)blockIdx.x * kStatsPerTile + tid] = acc;
-    }
-  } else {  // kEpiNormKnown: (x - mean) * istd and SpecAugment fill at store
-    const int* mk = p.masks ? p.masks + (long long)td.utt * (p.n_fmask + p.n_tmask) * 2 : nullptr;
-    const float mv = p.mask_value ? p.mask_value[td.utt] : 0.f;
-    for (int e = tid; e < rows * kMel; e += kThreads) {
-      const int f = e / kMel, m = e - f * kMel;
-      float y = p.pad_value;
-      if (f < nf) {
-        y = (sOut[f * kOutStride + m] - p.g_mean[m]) * p.g_istd[m];
-        if (mk != nullptr) {
-          const int t = frame0 + f;
-          bool masked = false;
-          for (int i = 0; i < p.n_fmask; ++i) masked |= (unsigned)(m - mk[2 * i]) < (unsigned)mk[2 * i + 1];
-          for (int i = p.n_fmask; i < p.n_fmask + p.n_tmask; ++i)
-            masked |= (unsigned)(t - mk[2 * i]) < (unsigned)mk[2 * i + 1];
-          if (masked) y = mv;
+            default:
+              break;
+          }
         }
       }
-      out_tile[e] = y;
+      __syncthreads();
+
+      // ---- phase 4: store.  Warp w owns rows 4w..4w+3; lane owns columns lane, lane+32, lane+64 -------
+      {
+        const bool c2ok = lane < kMel - 64;
+        if (p.epilogue == kEpiRaw) {
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int f = 4 * warp + i;
+            if (f < rows) {
+              const bool valid = f < nf;
+              const float* src = sOut + f * kOutStride + lane;
+              float* dst = out_tile + f * kMel + lane;
+              const float x0 = valid ? src[0] : p.pad_value;
+              const float x1 = valid ? src[32] : p.pad_value;
+              const float x2 = (valid && c2ok) ? src[64] : p.pad_value;
+              dst[0] = x0;
+              dst[32] = x1;
+              if (c2ok) dst[64] = x2;
+              if (valid) {
+                s0 += x0; q0 = fmaf(x0, x0, q0);
+                s1 += x1; q1 = fmaf(x1, x1, q1);
+                s2 += x2; q2 = fmaf(x2, x2, q2);
+              }
+            }
+          }
+          if (p.tile_stats != nullptr) {
+            // per-warp partial column sums -> shared -> fixed-order sum over the 8 warps (deterministic)
+            float* st = sStat + warp * kStatsPerTile;
+            st[lane] = s0; st[lane + 32] = s1;
+            st[kMel + lane] = q0; st[kMel + lane + 32] = q1;
+            if (c2ok) { st[lane + 64] = s2; st[kMel + lane + 64] = q2; }
+            __syncthreads();
+            if (tid < kStatsPerTile) {
+              float acc = 0.f;
+#pragma unroll
+              for (int w = 0; w < kWarps; ++w) acc += sStat[w * kStatsPerTile + tid];
+              p.tile_stats[(long long)tile * kStatsPerTile + tid] = acc;
+            }
+          }
+        } else {  // kEpiNormKnown: (x - mean) * istd and SpecAugment fill at store
+          const int* mk = p.masks ? p.masks + (long long)cur.utt * (p.n_fmask + p.n_tmask) * 2 : nullptr;
+          const float mv = p.mask_value ? p.mask_value[cur.utt] : 0.f;
+          float mu[3], is[3];
+          bool cm[3] = {false, false, false};
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int m = min(lane + 32 * c, kMel - 1);
+            mu[c] = p.g_mean[m];
+            is[c] = p.g_istd[m];
+            if (mk != nullptr)
+              for (int i = 0; i < p.n_fmask; ++i) cm[c] |= (unsigned)(m - mk[2 * i]) < (unsigned)mk[2 * i + 1];
+          }
+#pragma unroll 1
+          for (int i = 0; i < 4; ++i) {
+            const int f = 4 * warp + i;
+            if (f < rows) {
+              const bool valid = f < nf;
+              bool trow = false;
+              if (mk != nullptr) {
+                const int t = cur.frame0 + f;
+                for (int k = p.n_fmask; k < p.n_fmask + p.n_tmask; ++k)
+                  trow |= (unsigned)(t - mk[2 * k]) < (unsigned)mk[2 * k + 1];
+              }
+              const float* src = sOut + f * kOutStride + lane;
+              float* dst = out_tile + f * kMel + lane;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                if (c < 2 || c2ok) {
+                  float y = p.pad_value;
+                  if (valid) {
+                    y = (src[32 * c] - mu[c]) * is[c];
+                    if (trow || cm[c]) y = mv;
+                  }
+                  dst[32 * c] = y;
+                }
+              }
+            }
+          }
+        }
+      }
     }
+    if (!has_next) break;
+    __syncthreads();  // sD / sOut / sStat are rewritten by the next tile
+    tile = next_tile;
+    cur = nxt;
   }
 }
 
@@ -388,13 +608,10 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
 // =====================================================================================================
 __global__ void __launch_bounds__(kThreads) feature_tile_kernel(const FbankLaunch p) {
   const TileDesc td = p.tiles[blockIdx.x];
-  const UttDesc ud = p.utts[td.utt];
-  const int frame0 = td.frame0;
-  const int nf = max(0, min(kTileFrames, ud.n_frames - frame0));
-  const int rows = p.pad_tmax > 0 ? min(kTileFrames, p.pad_tmax - frame0) : nf;
-  const float* __restrict__ in_tile =
-      reinterpret_cast<const float*>(p.pcm + ud.pcm_byte_off) + (long long)frame0 * kMel;
-  float* __restrict__ out_tile = p.out + (ud.out_row + frame0) * (long long)kMel;
+  const int nf = td.nf;
+  const int rows = td.rows;
+  const float* __restrict__ in_tile = reinterpret_cast<const float*>(p.pcm + td.src_byte_off);
+  float* __restrict__ out_tile = p.out + td.out_row0 * (long long)kMel;
   const int tid = threadIdx.x;
   if (in_tile != out_tile || nf < rows) {
     for (int e = tid; e < rows * kMel; e += kThreads) out_tile[e] = (e < nf * kMel) ? in_tile[e] : p.pad_value;
@@ -526,11 +743,10 @@ __global__ void __launch_bounds__(128) finalize_utt_kernel(const FinalizeLaunch 
 // =====================================================================================================
 __global__ void __launch_bounds__(kThreads) apply_kernel(const ApplyLaunch p) {
   const TileDesc td = p.tiles[blockIdx.x];
-  const UttDesc ud = p.utts[td.utt];
   const int frame0 = td.frame0;
-  const int nf = max(0, min(kTileFrames, ud.n_frames - frame0));
-  const int rows = p.pad_tmax > 0 ? min(kTileFrames, p.pad_tmax - frame0) : nf;
-  float4* __restrict__ o4 = reinterpret_cast<float4*>(p.out + (ud.out_row + frame0) * (long long)kMel);
+  const int nf = td.nf;
+  const int rows = td.rows;
+  float4* __restrict__ o4 = reinterpret_cast<float4*>(p.out + td.out_row0 * (long long)kMel);
   const long long so = p.shared_stats ? 0 : (long long)td.utt * kMel;
   const float4* mean4 = reinterpret_cast<const float4*>(p.mean + so);
   const float4* istd4 = reinterpret_cast<const float4*>(p.istd + so);
@@ -636,7 +852,14 @@ cudaError_t launch_fbank(const FbankLaunch& p, cudaStream_t s) {
     configured = true;
   }
   if (p.n_tiles <= 0) return cudaSuccess;
-  fbank_tile_kernel<<<p.n_tiles, kThreads, kSmemBytes, s>>>(p);
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int grid = p.n_tiles < 2 * n_sm ? p.n_tiles : 2 * n_sm;  // persistent: 2 resident CTAs per SM
+  fbank_tile_kernel<<<grid, kThreads, kSmemBytes, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -26,9 +26,16 @@ struct UttDesc {
   int flags;               // bit0: PCM is fp32 in [-1,1) (scaled by 2^15 on load), else int16
 };
 
+// One tile = up to 32 consecutive frames of one utterance (32 bytes; everything the fbank kernel
+// needs, so that a persistent CTA fetches its next work item with a single load).
 struct TileDesc {
+  long long src_byte_off;  // PCM: byte offset of the tile's first sample; features: of its first row
+  long long out_row0;      // first output row of the tile
   int utt;
-  int frame0;  // first frame of the tile inside the utterance; >= n_frames => pure padding tile
+  int frame0;              // first frame of the tile inside the utterance
+  int nf;                  // valid frames in the tile (0 => pure padding tile of the padded layout)
+  short rows;              // output rows the tile owns (>= nf; the rest is padding)
+  short flags;             // bit0: PCM is fp32
 };
 
 // device-side tables owned by a context
