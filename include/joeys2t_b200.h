@@ -136,9 +136,18 @@ int js2t_features_execute(js2t_plan* plan, const float* feats_dev, float* out_de
 int js2t_plan_enable_profiling(js2t_plan* plan, int n_slots);
 int js2t_plan_kernel_times_ms(js2t_plan* plan, float* ms_out, int n, int* n_written);
 
+/* Tuning / test switches.  "force_unfused" = 1 makes utterance CMVN use the three-kernel path
+ * (fbank+stats, finalize, apply) instead of the single fused persistent kernel. */
+int js2t_plan_set_option(js2t_plan* plan, const char* name, int value);
+/* With option "debug_times" = 1: per-tile %globaltimer stamps [n_tiles][4] (tile start, stored,
+ * published, normalised-older-tile) of the last execute, copied to host memory (synchronous). */
+int js2t_plan_debug_times(const js2t_plan* plan, unsigned long long* host_out, int64_t n_values);
+
 /* Device pointer to the per-utterance fp64 statistics [n_utts][160] (sum | sum of squares of the
  * raw log-mel) produced by the last execute in UTTERANCE / STATS_ONLY / masked modes. */
 int js2t_plan_utt_stats(const js2t_plan* plan, const double** stats_dev);
+/* Same, copied (device to device, on `stream`) into a caller-owned buffer of n_utts * 160 doubles. */
+int js2t_plan_copy_utt_stats(const js2t_plan* plan, double* dst_dev, void* stream);
 
 /* ---- global CMVN (multi-GPU) ----------------------------------------------------------------
  * accum_dev: 161 doubles on the device = per-bin sum[80] | sumsq[80] | frame count.

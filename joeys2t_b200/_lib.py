@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "js2t_plan_total_frames", "js2t_plan_out_rows", "js2t_plan_get_frames", "js2t_plan_get_out_rows",
     "js2t_plan_set_cmvn", "js2t_plan_set_global_stats", "js2t_plan_set_masks", "js2t_fbank_execute",
     "js2t_features_execute", "js2t_plan_enable_profiling", "js2t_plan_kernel_times_ms",
-    "js2t_plan_utt_stats", "js2t_global_stats_accumulate",
+    "js2t_plan_set_option", "js2t_plan_debug_times", "js2t_plan_utt_stats", "js2t_plan_copy_utt_stats", "js2t_global_stats_accumulate",
     "js2t_global_stats_allreduce", "js2t_global_stats_finalize", "js2t_normalize_execute",
 ]
 
@@ -104,7 +104,10 @@ def _declare(lib):
     lib.js2t_features_execute.argtypes = [vp, vp, vp, vp]
     lib.js2t_plan_enable_profiling.argtypes = [vp, i32]
     lib.js2t_plan_kernel_times_ms.argtypes = [vp, vp, i32, P(i32)]
+    lib.js2t_plan_set_option.argtypes = [vp, c.c_char_p, i32]
+    lib.js2t_plan_debug_times.argtypes = [vp, vp, i64]
     lib.js2t_plan_utt_stats.argtypes = [vp, P(vp)]
+    lib.js2t_plan_copy_utt_stats.argtypes = [vp, vp, vp]
     lib.js2t_global_stats_accumulate.argtypes = [vp, vp, vp]
     lib.js2t_global_stats_allreduce.argtypes = [vp, vp, vp]
     lib.js2t_global_stats_finalize.argtypes = [vp, vp, vp]

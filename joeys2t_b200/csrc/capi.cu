@@ -64,6 +64,11 @@ struct js2t_plan {
   float* d_gmean = nullptr;
   float* d_gistd = nullptr;
   double* d_utt_stats = nullptr;
+  int* d_counter = nullptr;  // [n_utts] fused-CMVN tile counters (zero between launches)
+  int* d_flag = nullptr;     // [n_utts] fused-CMVN completion flags (hold the epoch of the last launch)
+  int* d_sched = nullptr;    // [2] tile scheduler counters of the persistent kernel (self-resetting)
+  int epoch = 0;
+  int max_utt_tiles = 0;
   int* d_masks = nullptr;
   size_t masks_cap = 0;
   // configuration
@@ -72,6 +77,8 @@ struct js2t_plan {
   float mask_value_const = 0.f;
   bool has_masks = false, global_stats_set = false, stats_valid = false;
   bool feature_input = false;  // rows of 80 floats instead of PCM (js2t_plan_create_features)
+  bool force_unfused = false;  // testing / profiling: use the three-kernel CMVN path
+  unsigned long long* d_dbg = nullptr;  // [n_tiles][4] debug time stamps (option "debug_times")
   // optional instrumentation: CUDA events around the fbank kernel of each execute (ring of slots)
   std::vector<cudaEvent_t> prof_ev;  // 2 per slot
   long long prof_calls = 0;
@@ -254,9 +261,13 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
       t.out_row0 = d.out_row + f0;
       t.utt = u;
       t.frame0 = f0;
-      t.nf = d.n_frames - f0 < 0 ? 0 : (d.n_frames - f0 > kTileFrames ? kTileFrames : d.n_frames - f0);
-      t.rows = (short)(span - f0 > kTileFrames ? kTileFrames : span - f0);
-      t.flags = (short)(d.flags & 1);
+      t.utt_tiles = (d.n_frames + kTileFrames - 1) / kTileFrames;
+      const int nfv = d.n_frames - f0 < 0 ? 0 : (d.n_frames - f0 > kTileFrames ? kTileFrames : d.n_frames - f0);
+      t.nf = (unsigned char)nfv;
+      t.rows = (unsigned char)(span - f0 > kTileFrames ? kTileFrames : span - f0);
+      t.flags = (unsigned char)(d.flags & 1);
+      t.pad_ = 0;
+      if (t.utt_tiles > p->max_utt_tiles) p->max_utt_tiles = t.utt_tiles;
       tiles.push_back(t);
     }
   }
@@ -274,6 +285,9 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
   const size_t o_mv = carve(sizeof(float) * n_utts);
   const size_t o_g = carve(sizeof(float) * 2 * kMel);
   const size_t o_ustats = carve(sizeof(double) * kStatsPerTile * n_utts);
+  const size_t o_counter = carve(sizeof(int) * n_utts);
+  const size_t o_flag = carve(sizeof(int) * n_utts);
+  const size_t o_sched = carve(sizeof(int) * 2);
   cudaSetDevice(ctx->device);
   cudaError_t e = cudaMalloc(&p->d_ws, off);
   if (e != cudaSuccess) {
@@ -290,7 +304,11 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
   p->d_gmean = reinterpret_cast<float*>(base + o_g);
   p->d_gistd = p->d_gmean + kMel;
   p->d_utt_stats = reinterpret_cast<double*>(base + o_ustats);
-  e = cudaMemcpy(p->d_utts, p->h_utts.data(), sizeof(UttDesc) * n_utts, cudaMemcpyHostToDevice);
+  p->d_counter = reinterpret_cast<int*>(base + o_counter);
+  p->d_flag = reinterpret_cast<int*>(base + o_flag);
+  p->d_sched = reinterpret_cast<int*>(base + o_sched);
+  e = cudaMemset(p->d_counter, 0, (o_sched - o_counter) + sizeof(int) * 2);
+  if (e == cudaSuccess) e = cudaMemcpy(p->d_utts, p->h_utts.data(), sizeof(UttDesc) * n_utts, cudaMemcpyHostToDevice);
   if (e == cudaSuccess)
     e = cudaMemcpy(p->d_tiles, tiles.data(), sizeof(TileDesc) * tiles.size(), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
@@ -321,6 +339,7 @@ int js2t_plan_destroy(js2t_plan* plan) {
   cudaSetDevice(plan->ctx->device);
   for (cudaEvent_t e : plan->prof_ev) cudaEventDestroy(e);
   if (plan->d_masks) cudaFree(plan->d_masks);
+  if (plan->d_dbg) cudaFree(plan->d_dbg);
   if (plan->d_ws) cudaFree(plan->d_ws);
   delete plan;
   return JS2T_OK;
@@ -470,6 +489,7 @@ static int run_pipeline(js2t_plan* plan, const void* in_dev, float* out_dev, cud
   f.utts = plan->d_utts;
   f.tiles = plan->d_tiles;
   f.n_tiles = plan->n_tiles;
+  f.sched = plan->d_sched;
   if (from_pcm) f.tab = tables_of(plan->ctx);
   f.out = out_dev;
   f.pad_tmax = plan->pad_tmax;
@@ -512,8 +532,33 @@ static int run_pipeline(js2t_plan* plan, const void* in_dev, float* out_dev, cud
     plan->stats_valid = false;
     return JS2T_OK;
   }
-  // (3) raw log-mel + per-tile statistics -> per-utterance finalize -> in-place apply
+  // (3a) utterance CMVN (before SpecAugment), every utterance short enough that its tiles are in flight
+  //      together: statistics, finalisation and normalisation all inside the persistent fbank kernel
   f.tile_stats = plan->d_tile_stats;
+  if (from_pcm && mode == JS2T_CMVN_UTTERANCE && (plan->before || !masks) &&
+      plan->max_utt_tiles <= fbank_persistent_grid() && !plan->force_unfused) {
+    f.fused = 1;
+    f.epoch = ++plan->epoch;
+    f.norm_means = plan->norm_means;
+    f.norm_vars = plan->norm_vars;
+    f.mask_value_mode = plan->mask_value_mode;
+    f.mask_value_const = plan->mask_value_const;
+    f.masks = masks ? plan->d_masks : nullptr;
+    f.n_fmask = masks ? plan->n_fmask : 0;
+    f.n_tmask = masks ? plan->n_tmask : 0;
+    f.utt_counter = plan->d_counter;
+    f.utt_flag = plan->d_flag;
+    f.norm_mean = plan->d_mean;
+    f.norm_istd = plan->d_istd;
+    f.utt_mask_value = plan->d_mask_value;
+    f.stats_out = plan->d_utt_stats;
+    f.dbg_times = plan->d_dbg;
+    JS2T_CUDA(launch_main(f));
+    plan->stats_valid = true;
+    return JS2T_OK;
+  }
+  f.dbg_times = plan->d_dbg;
+  // (3b) raw log-mel + per-tile statistics -> per-utterance finalize -> in-place apply
   JS2T_CUDA(launch_main(f));
   const bool shared = (mode == JS2T_CMVN_GLOBAL);
   FinalizeLaunch z = make_finalize(plan, out_dev, shared);
@@ -559,6 +604,44 @@ int js2t_plan_kernel_times_ms(js2t_plan* plan, float* ms_out, int n, int* n_writ
     ms_out[w++] = ms;
   }
   *n_written = w;
+  return JS2T_OK;
+}
+
+int js2t_plan_set_option(js2t_plan* plan, const char* name, int value) {
+  if (plan == nullptr || name == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
+  if (strcmp(name, "force_unfused") == 0) {
+    plan->force_unfused = value != 0;
+    return JS2T_OK;
+  }
+  if (strcmp(name, "debug_times") == 0) {
+    JS2T_CUDA(cudaSetDevice(plan->ctx->device));
+    if (value != 0 && plan->d_dbg == nullptr) {
+      JS2T_CUDA(cudaMalloc(&plan->d_dbg, sizeof(unsigned long long) * 4 * plan->n_tiles));
+      JS2T_CUDA(cudaMemset(plan->d_dbg, 0, sizeof(unsigned long long) * 4 * plan->n_tiles));
+    } else if (value == 0 && plan->d_dbg != nullptr) {
+      cudaFree(plan->d_dbg);
+      plan->d_dbg = nullptr;
+    }
+    return JS2T_OK;
+  }
+  return fail(JS2T_ERR_INVALID, "unknown option '%s'", name);
+}
+
+int js2t_plan_debug_times(const js2t_plan* plan, unsigned long long* host_out, int64_t n_values) {
+  if (plan == nullptr || host_out == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
+  if (plan->d_dbg == nullptr) return fail(JS2T_ERR_STATE, "option debug_times is off");
+  if (n_values > 4ll * plan->n_tiles) n_values = 4ll * plan->n_tiles;
+  JS2T_CUDA(cudaSetDevice(plan->ctx->device));
+  JS2T_CUDA(cudaMemcpy(host_out, plan->d_dbg, sizeof(unsigned long long) * n_values, cudaMemcpyDeviceToHost));
+  return JS2T_OK;
+}
+
+int js2t_plan_copy_utt_stats(const js2t_plan* plan, double* dst_dev, void* stream) {
+  if (plan == nullptr || dst_dev == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
+  if (!plan->stats_valid) return fail(JS2T_ERR_STATE, "no statistics: run js2t_fbank_execute in a statistics mode first");
+  JS2T_CUDA(cudaSetDevice(plan->ctx->device));
+  JS2T_CUDA(cudaMemcpyAsync(dst_dev, plan->d_utt_stats, sizeof(double) * kStatsPerTile * plan->n_utts,
+                            cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return JS2T_OK;
 }
 

@@ -282,6 +282,122 @@ __device__ __forceinline__ void prefetch_tile(const FbankLaunch& p, const TileDe
   tma_load_1d(sRaw + 16 - lead, p.pcm + t.src_byte_off - lead, bytes, bar);
 }
 
+// ---- fused utterance CMVN helpers -------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define JS2T_STAMP(slot)                                                                     \
+  if (p.dbg_times != nullptr && tid == 0) p.dbg_times[(long long)tile * 4 + (slot)] = globaltimer_ns();
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Executed by the whole CTA that published the last tile of utterance `utt`: per-bin sums over the
+// utterance's tiles in tile order (deterministic), then mean / inverse std (data_augmentation.py:96-109)
+// and the SpecAugment fill value (mean of the CMVN output, :45-46).
+// fixed-order (tile 0, 1, 2, ...) fp64 sum of one statistics column over n tiles, loads batched by 8
+__device__ __forceinline__ double sum_tile_column(const float* ts, int n) {
+  double acc = 0.0;
+  int i = 0;
+  for (; i + 8 <= n; i += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldcg(ts + (long long)(i + j) * kStatsPerTile);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += (double)v[j];
+  }
+  for (; i < n; ++i) acc += (double)__ldcg(ts + (long long)i * kStatsPerTile);
+  return acc;
+}
+
+__device__ void finalize_utterance_in_kernel(const FbankLaunch& p, const TileDesc& t, int tile, float* sScratch) {
+  const int tid = threadIdx.x;
+  const int first_tile = tile - t.frame0 / kTileFrames;
+  const int T = p.utts[t.utt].n_frames;
+  double* sRed = reinterpret_cast<double*>(sScratch);  // [160] column sums, then [80] column means
+  if (tid < kStatsPerTile) {
+    const double acc = sum_tile_column(p.tile_stats + (long long)first_tile * kStatsPerTile + tid, t.utt_tiles);
+    sRed[tid] = acc;
+    if (p.stats_out != nullptr) p.stats_out[(long long)t.utt * kStatsPerTile + tid] = acc;
+  }
+  __syncthreads();
+  double col = 0.0;
+  if (tid < kMel) {
+    const double S = sRed[tid], Q = sRed[kMel + tid];
+    const double mu = S / T;
+    double mean = 0.0, istd = 1.0;
+    if (p.norm_means) mean = (double)(float)mu;
+    if (p.norm_vars) istd = 1.0 / sqrt(fmax(Q / T - mu * mu, 1e-10));
+    p.norm_mean[(long long)t.utt * kMel + tid] = (float)mean;
+    p.norm_istd[(long long)t.utt * kMel + tid] = (float)istd;
+    col = (mu - mean) * istd;  // column mean of the normalised utterance
+  }
+  __syncthreads();
+  if (tid < kMel) sRed[tid] = col;
+  __syncthreads();
+  if (tid == 0) {
+    double acc = 0.0;
+    for (int i = 0; i < kMel; ++i) acc += sRed[i];
+    p.utt_mask_value[t.utt] = (p.mask_value_mode == 1) ? p.mask_value_const : (float)(acc / kMel);
+  }
+}
+
+// Wait until the utterance of tile `t` has been finalised, then (x - mean) * istd (+ SpecAugment fill)
+// in place on that tile, which this CTA wrote earlier (L2-resident).  Whole CTA; sNorm: 160 floats.
+__device__ __forceinline__ void normalize_tile_in_kernel(const FbankLaunch& p, const TileDesc& t, float* sNorm) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    while (ld_acquire(p.utt_flag + t.utt) != p.epoch) __nanosleep(32);
+  }
+  __syncthreads();
+  if (tid < kStatsPerTile) {
+    const float* src = tid < kMel ? p.norm_mean + (long long)t.utt * kMel + tid
+                                  : p.norm_istd + (long long)t.utt * kMel + (tid - kMel);
+    sNorm[tid] = __ldcg(src);
+  }
+  __syncthreads();
+  const int n_masks = p.n_fmask + p.n_tmask;
+  const int* mk = (p.masks != nullptr) ? p.masks + (long long)t.utt * n_masks * 2 : nullptr;
+  const float mv = (mk != nullptr) ? __ldcg(p.utt_mask_value + t.utt) : 0.f;
+  float4* o4 = reinterpret_cast<float4*>(p.out + t.out_row0 * (long long)kMel);
+  const float4* mu4 = reinterpret_cast<const float4*>(sNorm);
+  const float4* is4 = reinterpret_cast<const float4*>(sNorm + kMel);
+  const int n4 = (int)t.nf * (kMel / 4);
+  for (int e = tid; e < n4; e += kThreads) {
+    const int f = e / (kMel / 4), c4 = e - f * (kMel / 4);
+    const float4 x = __ldcg(o4 + e);
+    const float4 mu = mu4[c4], is = is4[c4];
+    float4 y = make_float4((x.x - mu.x) * is.x, (x.y - mu.y) * is.y, (x.z - mu.z) * is.z, (x.w - mu.w) * is.w);
+    if (mk != nullptr) {
+      const int tt = t.frame0 + f;
+      bool trow = false;
+      for (int i = p.n_fmask; i < n_masks; ++i) trow |= (unsigned)(tt - mk[2 * i]) < (unsigned)mk[2 * i + 1];
+      bool m0 = trow, m1 = trow, m2 = trow, m3 = trow;
+      for (int i = 0; i < p.n_fmask; ++i) {
+        const int f0 = mk[2 * i];
+        const unsigned w = (unsigned)mk[2 * i + 1];
+        m0 |= (unsigned)(4 * c4 + 0 - f0) < w;
+        m1 |= (unsigned)(4 * c4 + 1 - f0) < w;
+        m2 |= (unsigned)(4 * c4 + 2 - f0) < w;
+        m3 |= (unsigned)(4 * c4 + 3 - f0) < w;
+      }
+      if (m0) y.x = mv;
+      if (m1) y.y = mv;
+      if (m2) y.z = mv;
+      if (m3) y.w = mv;
+    }
+    o4[e] = y;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaunch p) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* sD = reinterpret_cast<float*>(smem + kOffD);
@@ -308,19 +424,47 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
   if (tid == 0) mbar_init(sBar, 1);
   __syncthreads();
 
-  int tile = blockIdx.x;
-  const int G = gridDim.x;
-  TileDesc cur = p.tiles[tile];  // grid <= n_tiles
+  // ---- dynamic tile scheduler: tiles are handed out in order by one global counter.  The two CTAs
+  // resident on an SM do not run at the same speed (the warp scheduler favours one of them by ~25 %),
+  // so a static round-robin split leaves the slower half of the grid as stragglers.  Each CTA holds
+  // the tile it computes (cur), the one whose PCM is being prefetched (next) and one claimed index
+  // further ahead whose descriptor load is in flight.
+  __shared__ int sClaim[2];
+  if (tid == 0) {
+    const int a = atomicAdd(p.sched, 2);
+    sClaim[0] = a;
+    sClaim[1] = a + 1;
+  }
+  __syncthreads();
+  int tile = sClaim[0];
+  int next_tile = sClaim[1];
+  if (tile >= p.n_tiles) {  // more CTAs than tiles
+    if (tid == 0 && atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+      p.sched[0] = 0;
+      p.sched[1] = 0;
+    }
+    return;
+  }
+  TileDesc cur = p.tiles[tile];
+  TileDesc nxt = cur;
+  if (next_tile < p.n_tiles) nxt = p.tiles[next_tile];
   unsigned parity = 0;
+  // fused CMVN: tiles this CTA has written and not yet normalised (their utterances' statistics may
+  // still be in flight in other CTAs)
+  constexpr int kMaxPend = 4;
+  __shared__ TileDesc sPend[kMaxPend];
+  __shared__ int sPendTile[kMaxPend];
+  int n_pend = 0;
+  __shared__ int sIsLast;
   if (tid == 0 && cur.nf > 0 && !(cur.flags & 1)) prefetch_tile(p, cur, sRaw, sBar);
 
   while (true) {
-    const int next_tile = tile + G;
+    __syncthreads();  // sClaim was read by everyone
+    if (tid == 0) sClaim[0] = atomicAdd(p.sched, 1);  // claim two ahead; consumed at the end of the iteration
     const bool has_next = next_tile < p.n_tiles;
-    TileDesc nxt = cur;
-    if (has_next) nxt = p.tiles[next_tile];  // consumed one iteration later: latency hidden
     const bool next_tma = has_next && nxt.nf > 0 && !(nxt.flags & 1);
 
+    JS2T_STAMP(0)
     const int nf = cur.nf;      // valid frames in this tile
     const int rows = cur.rows;  // rows owned in the output (padded layout: the tail is padding)
     float* __restrict__ out_tile = p.out + cur.out_row0 * (long long)kMel;
@@ -594,10 +738,78 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
         }
       }
     }
+    JS2T_STAMP(1)
+    if (!p.fused && p.dbg_times != nullptr && tid == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      p.dbg_times[(long long)tile * 4 + 2] = smid;
+    }
+    if (p.fused) {
+      if (nf > 0) {
+        // publish this tile: raw rows + per-tile statistics are written; count it for its utterance
+        __syncthreads();
+        if (tid == 0) {
+          __threadfence();
+          sIsLast = (atomicAdd(p.utt_counter + cur.utt, 1) == cur.utt_tiles - 1);
+        }
+        __syncthreads();
+        if (sIsLast) {  // CTA-uniform
+          __threadfence();
+          finalize_utterance_in_kernel(p, cur, tile, sStat);
+          __threadfence();
+          __syncthreads();
+          if (tid == 0) {
+            p.utt_counter[cur.utt] = 0;  // ready for the next launch
+            st_release(p.utt_flag + cur.utt, p.epoch);
+          }
+        }
+      }
+      JS2T_STAMP(2)
+      if (nf > 0) {
+        if (tid == 0) {
+          sPend[n_pend] = cur;
+          sPendTile[n_pend] = tile;
+        }
+        ++n_pend;
+      }
+      // Normalise older tiles whose utterance lies entirely before the tile this CTA computes next:
+      // then no CTA that the utterance still depends on can itself be waiting for one of our tiles
+      // (deadlock-free), and with tiles handed out in order its statistics are normally complete.
+      __syncthreads();
+      while (n_pend > 0) {
+        const int first = sPendTile[0] - sPend[0].frame0 / kTileFrames;
+        const int last = first + sPend[0].utt_tiles - 1;
+        if (!(next_tile > last || !has_next || n_pend == kMaxPend)) break;
+        normalize_tile_in_kernel(p, sPend[0], sStat);
+        __syncthreads();
+        if (tid == 0) {
+          for (int i = 1; i < n_pend; ++i) {
+            sPend[i - 1] = sPend[i];
+            sPendTile[i - 1] = sPendTile[i];
+          }
+        }
+        --n_pend;
+        __syncthreads();
+      }
+      JS2T_STAMP(3)
+    }
     if (!has_next) break;
-    __syncthreads();  // sD / sOut / sStat are rewritten by the next tile
+    __syncthreads();  // sD / sOut / sStat are rewritten by the next tile; sClaim[0] is visible
     tile = next_tile;
     cur = nxt;
+    next_tile = sClaim[0];
+    if (next_tile < p.n_tiles) nxt = p.tiles[next_tile];  // first used after the next tile's staging phase
+  }
+  if (p.fused) {  // drain
+    for (int i = 0; i < n_pend; ++i) {
+      __syncthreads();
+      normalize_tile_in_kernel(p, sPend[i], sStat);
+    }
+  }
+  // the last CTA to leave re-arms the scheduler for the next launch
+  if (tid == 0 && atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+    p.sched[0] = 0;
+    p.sched[1] = 0;
   }
 }
 
@@ -644,10 +856,8 @@ __global__ void __launch_bounds__(128) finalize_utt_kernel(const FinalizeLaunch 
   double S = 0.0, Q = 0.0;
   if (b < kMel) {
     const float* ts = p.tile_stats + (long long)ud.tile_start * kStatsPerTile;
-    for (int t = 0; t < n_tiles; ++t) {  // fixed order: deterministic
-      S += (double)ts[(long long)t * kStatsPerTile + b];
-      Q += (double)ts[(long long)t * kStatsPerTile + kMel + b];
-    }
+    S = sum_tile_column(ts + b, n_tiles);  // fixed order: deterministic
+    Q = sum_tile_column(ts + kMel + b, n_tiles);
     if (p.stats_out != nullptr) {
       p.stats_out[(long long)u * kStatsPerTile + b] = S;
       p.stats_out[(long long)u * kStatsPerTile + kMel + b] = Q;
@@ -844,21 +1054,32 @@ cudaError_t upload_mel_weights(const float* wu256, const float* wd256, cudaStrea
   return cudaMemcpyToSymbolAsync(c_mel_wd, wd256, 256 * sizeof(float), 0, cudaMemcpyHostToDevice, s);
 }
 
-cudaError_t launch_fbank(const FbankLaunch& p, cudaStream_t s) {
-  static bool configured = false;  // per process; the attribute is per device function
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(fbank_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  if (p.n_tiles <= 0) return cudaSuccess;
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
+static int g_fbank_grid = 0;
+
+int fbank_persistent_grid() {
+  if (g_fbank_grid == 0) {
+    int dev = 0, n_sm = 0, occ = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(fbank_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fbank_tile_kernel, kThreads, kSmemBytes);
+    if (occ < 1) occ = 1;
+    g_fbank_grid = occ * n_sm;  // every CTA resident at once: one wave, persistent
   }
-  const int grid = p.n_tiles < 2 * n_sm ? p.n_tiles : 2 * n_sm;  // persistent: 2 resident CTAs per SM
+  return g_fbank_grid;
+}
+
+cudaError_t launch_fbank(const FbankLaunch& p, cudaStream_t s) {
+  if (p.n_tiles <= 0) return cudaSuccess;
+  const int full = fbank_persistent_grid();
+  const int grid = p.n_tiles < full ? p.n_tiles : full;
+  if (p.fused) {
+    // CTAs wait on each other's statistics: co-residency must be guaranteed
+    FbankLaunch copy = p;
+    void* args[] = {&copy};
+    return cudaLaunchCooperativeKernel((const void*)fbank_tile_kernel, dim3(grid), dim3(kThreads), args,
+                                       (size_t)kSmemBytes, s);
+  }
   fbank_tile_kernel<<<grid, kThreads, kSmemBytes, s>>>(p);
   return cudaGetLastError();
 }

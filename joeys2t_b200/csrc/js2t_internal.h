@@ -33,10 +33,13 @@ struct TileDesc {
   long long out_row0;      // first output row of the tile
   int utt;
   int frame0;              // first frame of the tile inside the utterance
-  int nf;                  // valid frames in the tile (0 => pure padding tile of the padded layout)
-  short rows;              // output rows the tile owns (>= nf; the rest is padding)
-  short flags;             // bit0: PCM is fp32
+  int utt_tiles;           // number of non-empty tiles of this utterance
+  unsigned char nf;        // valid frames in the tile (0 => pure padding tile of the padded layout)
+  unsigned char rows;      // output rows the tile owns (>= nf; the rest is padding)
+  unsigned char flags;     // bit0: PCM is fp32
+  unsigned char pad_;
 };
+static_assert(sizeof(TileDesc) == 32, "TileDesc is loaded with two 16-byte loads");
 
 // device-side tables owned by a context
 struct DeviceTables {
@@ -55,6 +58,7 @@ struct FbankLaunch {
   const UttDesc* utts;
   const TileDesc* tiles;
   int n_tiles;
+  int* sched;         // [2] dynamic tile scheduler: next tile to hand out | CTAs that have left (self-resetting)
   DeviceTables tab;
   float* out;
   float* tile_stats;  // [n_tiles][160] or nullptr
@@ -68,6 +72,21 @@ struct FbankLaunch {
   const int* masks;     // [n_utts][n_masks][2] (start, width); first n_fmask are frequency masks
   int n_fmask, n_tmask;
   const float* mask_value;  // [n_utts]
+  // fused utterance CMVN (kEpiRaw + fused != 0): the CTA that completes an utterance's last tile
+  // reduces the per-tile statistics (fixed order), publishes mean / 1/std / fill value and raises the
+  // utterance's flag; every CTA normalises the tile it wrote one iteration earlier once that flag is up.
+  int fused;
+  int epoch;              // value a raised flag holds for this launch (no reset between launches)
+  int norm_means, norm_vars;
+  int mask_value_mode;    // 0: mean of the CMVN output, 1: constant
+  float mask_value_const;
+  int* utt_counter;       // [n_utts], zero between launches
+  int* utt_flag;          // [n_utts]
+  float* norm_mean;       // [n_utts][80]
+  float* norm_istd;       // [n_utts][80]
+  float* utt_mask_value;  // [n_utts]
+  double* stats_out;      // [n_utts][160] or nullptr
+  unsigned long long* dbg_times;  // [n_tiles][4] globaltimer stamps (debug / tuning only) or nullptr
 };
 
 struct FinalizeLaunch {
@@ -119,5 +138,6 @@ cudaError_t launch_global_finalize(const double* accum, int norm_means, int norm
                                    float* mean, float* istd, cudaStream_t s);
 cudaError_t launch_fill_value(float* dst, int n, float value, cudaStream_t s);
 int fbank_smem_bytes();
+int fbank_persistent_grid();  // CTAs of the persistent fbank kernel on the current device
 
 }  // namespace js2t

@@ -201,6 +201,19 @@ class Plan:
         _lib.check(fn(self._h, src.data_ptr(), out.data_ptr(), _stream_ptr()))
         return out
 
+    def set_option(self, name: str, value: int) -> "Plan":
+        _lib.check(self._lib.js2t_plan_set_option(self._h, name.encode(), int(value)))
+        return self
+
+    def debug_times(self) -> np.ndarray:
+        """(n_tiles, 4) uint64 %globaltimer stamps of the last execute (option "debug_times")."""
+        n_tiles = int(np.sum((np.maximum(self.n_frames, 1) + 31) // 32)) if self.layout == "ragged" \
+            else self.n_utts * ((self.pad_tmax + 31) // 32)
+        buf = np.zeros((n_tiles, 4), np.uint64)
+        torch.cuda.synchronize()
+        _lib.check(self._lib.js2t_plan_debug_times(self._h, buf.ctypes.data, buf.size))
+        return buf
+
     def enable_profiling(self, n_slots: int) -> None:
         _lib.check(self._lib.js2t_plan_enable_profiling(self._h, int(n_slots)))
 
@@ -213,14 +226,9 @@ class Plan:
 
     def utt_stats(self) -> torch.Tensor:
         """(B, 160) float64 per-utterance sum | sum of squares of the raw log-mel (a device copy)."""
-        p = ctypes.c_void_p()
-        _lib.check(self._lib.js2t_plan_utt_stats(self._h, ctypes.byref(p)))
         out = torch.empty((self.n_utts, 2 * NUM_MEL), dtype=torch.float64,
                           device=f"cuda:{self.ctx.device}")
-        rc = torch.cuda.cudart().cudaMemcpyAsync(out.data_ptr(), p.value, out.numel() * 8, 3,
-                                                 _stream_ptr())
-        if int(rc) != 0:
-            raise RuntimeError(f"cudaMemcpyAsync failed: {rc}")
+        _lib.check(self._lib.js2t_plan_copy_utt_stats(self._h, out.data_ptr(), _stream_ptr()))
         return out
 
     def accumulate_global(self, accum: torch.Tensor) -> None:
