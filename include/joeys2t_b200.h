@@ -136,8 +136,10 @@ int js2t_features_execute(js2t_plan* plan, const float* feats_dev, float* out_de
 int js2t_plan_enable_profiling(js2t_plan* plan, int n_slots);
 int js2t_plan_kernel_times_ms(js2t_plan* plan, float* ms_out, int n, int* n_written);
 
-/* Tuning / test switches.  "force_unfused" = 1 makes utterance CMVN use the three-kernel path
- * (fbank+stats, finalize, apply) instead of the single fused persistent kernel. */
+/* Tuning / test switches.  "fused_cmvn" = 1 runs utterance CMVN inside the persistent fbank kernel
+ * (the CTA that completes an utterance's last tile normalises it while it is L2-resident); the
+ * default is the three-kernel path (fbank + per-tile statistics, finalize, apply), which is the
+ * faster of the two on B200 today.  "debug_skip" only has an effect in -DJS2T_DBG=1 builds. */
 int js2t_plan_set_option(js2t_plan* plan, const char* name, int value);
 /* With option "debug_times" = 1: per-tile %globaltimer stamps [n_tiles][4] (tile start, stored,
  * published, normalised-older-tile) of the last execute, copied to host memory (synchronous). */

@@ -14,7 +14,8 @@ import threading
 from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
-LIB_PATH = CSRC / "libjoeys2t_b200.so"
+# JS2T_LIB selects another build of the same library (tuning A/B runs: tools/build_variant.py)
+LIB_PATH = Path(os.environ["JS2T_LIB"]).resolve() if os.environ.get("JS2T_LIB") else CSRC / "libjoeys2t_b200.so"
 SOURCES = ["fbank_kernels.cu", "capi.cu"]
 HEADERS = ["js2t_internal.h", "mel_structure.inc", "../../include/joeys2t_b200.h"]
 
@@ -54,6 +55,8 @@ def nvcc_command(out: Path = LIB_PATH, extra=()):
 
 
 def is_stale() -> bool:
+    if os.environ.get("JS2T_LIB"):
+        return False
     if not LIB_PATH.is_file():
         return True
     t = LIB_PATH.stat().st_mtime

@@ -75,6 +75,7 @@ constexpr int kOffBar = kOffRaw + ((kRawBytes + 15) / 16) * 16;
 constexpr int kSmemBytes = kOffBar + 16;
 static_assert(kOutFloats * 4 <= kWarps * kExchPerWarp * 8, "out tile aliases the exchange buffers");
 static_assert(kWarps * kStatsPerTile * 4 <= kDFloats * 4, "per-warp statistics alias the d buffer");
+static_assert(2 * kStatsPerTile * 8 + (2 * kMel + 4) * 4 <= kDFloats * 4, "fused-CMVN scratch aliases the d buffer");
 static_assert(kOffExch % 16 == 0 && kOffP % 16 == 0 && kOffTw256 % 16 == 0 && kOffWin % 16 == 0 &&
                   kOffRaw % 16 == 0 && kOffBar % 8 == 0,
               "alignment");
@@ -218,13 +219,39 @@ __device__ __forceinline__ int4 ldg_stream_int4(const void* p) {
 }
 
 // ---- mel stage: one run of consecutive filters [M0, M1), lane = frame ---------------------------------
+// FFT bins a run of filters needs: segments M0..M1 of the two-band structure (mel_structure.inc)
+__host__ __device__ constexpr int mel_bin_lo(int m0, int m1) {
+  int r = 1 << 30;
+#define JS2T_SEG(s, lo, hi) \
+  if ((s) >= m0 && (s) <= m1 && (lo) <= (hi) && (lo) < r) r = (lo);
+  JS2T_MEL_SEGMENTS(JS2T_SEG)
+#undef JS2T_SEG
+  return r;
+}
+__host__ __device__ constexpr int mel_bin_hi(int m0, int m1) {
+  int r = -1;
+#define JS2T_SEG(s, lo, hi) \
+  if ((s) >= m0 && (s) <= m1 && (lo) <= (hi) && (hi) > r) r = (hi);
+  JS2T_MEL_SEGMENTS(JS2T_SEG)
+#undef JS2T_SEG
+  return r;
+}
+
+// All of the run's power-spectrum values are loaded into registers first (one batch of independent
+// LDS), then the two slopes of every triangle are accumulated from registers: the shared-memory
+// latency is paid once per run instead of once per bin (the stores of the results would otherwise
+// order every later load behind them).
 template <int M0, int M1>
 __device__ __forceinline__ void mel_group(const float* __restrict__ Pl, float* __restrict__ orow) {
+  constexpr int KLO = mel_bin_lo(M0, M1), KHI = mel_bin_hi(M0, M1);
+  float pv[KHI - KLO + 1];
+#pragma unroll
+  for (int k = KLO; k <= KHI; ++k) pv[k - KLO] = Pl[k * kPStride];
   float lo_acc = 0.f, hi_acc = 0.f;
 #define JS2T_SEG(s, lo, hi)                                                          \
   if constexpr ((s) >= M0 && (s) <= M1) {                                            \
     _Pragma("unroll") for (int k = (lo); k <= (hi); ++k) {                           \
-      const float p = Pl[k * kPStride];                                              \
+      const float p = pv[k - KLO];                                                   \
       if constexpr ((s) < M1) hi_acc = fmaf(c_mel_wu[k], p, hi_acc);                 \
       if constexpr ((s) > M0) lo_acc = fmaf(c_mel_wd[k], p, lo_acc);                 \
     }                                                                                \
@@ -288,17 +315,15 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+// tuning builds only (-DJS2T_DBG=1): skip phases of the kernel (option "debug_skip"); the product
+// build compiles the tests out
+#if defined(JS2T_DBG) && JS2T_DBG
+#define JS2T_SKIP(bit) ((p.dbg_skip & (bit)) != 0)
+#else
+#define JS2T_SKIP(bit) false
+#endif
 #define JS2T_STAMP(slot)                                                                     \
   if (p.dbg_times != nullptr && tid == 0) p.dbg_times[(long long)tile * 4 + (slot)] = globaltimer_ns();
-
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release(int* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 // Executed by the whole CTA that published the last tile of utterance `utt`: per-bin sums over the
 // utterance's tiles in tile order (deterministic), then mean / inverse std (data_augmentation.py:96-109)
@@ -318,8 +343,10 @@ __device__ __forceinline__ double sum_tile_column(const float* ts, int n) {
   return acc;
 }
 
-__device__ void finalize_utterance_in_kernel(const FbankLaunch& p, const TileDesc& t, int tile, float* sScratch) {
+// Leaves mean[80] | istd[80] | fill value in sNorm (= sScratch + 160 doubles) for the normalisation.
+__device__ __noinline__ void finalize_utterance_in_kernel(const FbankLaunch& p, const TileDesc& t, int tile, float* sScratch) {
   const int tid = threadIdx.x;
+  float* sNorm = sScratch + 2 * kStatsPerTile;
   const int first_tile = tile - t.frame0 / kTileFrames;
   const int T = p.utts[t.utt].n_frames;
   double* sRed = reinterpret_cast<double*>(sScratch);  // [160] column sums, then [80] column means
@@ -338,6 +365,8 @@ __device__ void finalize_utterance_in_kernel(const FbankLaunch& p, const TileDes
     if (p.norm_vars) istd = 1.0 / sqrt(fmax(Q / T - mu * mu, 1e-10));
     p.norm_mean[(long long)t.utt * kMel + tid] = (float)mean;
     p.norm_istd[(long long)t.utt * kMel + tid] = (float)istd;
+    sNorm[tid] = (float)mean;
+    sNorm[kMel + tid] = (float)istd;
     col = (mu - mean) * istd;  // column mean of the normalised utterance
   }
   __syncthreads();
@@ -346,58 +375,69 @@ __device__ void finalize_utterance_in_kernel(const FbankLaunch& p, const TileDes
   if (tid == 0) {
     double acc = 0.0;
     for (int i = 0; i < kMel; ++i) acc += sRed[i];
-    p.utt_mask_value[t.utt] = (p.mask_value_mode == 1) ? p.mask_value_const : (float)(acc / kMel);
+    const float mv = (p.mask_value_mode == 1) ? p.mask_value_const : (float)(acc / kMel);
+    p.utt_mask_value[t.utt] = mv;
+    sNorm[2 * kMel] = mv;
   }
+  __syncthreads();
 }
 
-// Wait until the utterance of tile `t` has been finalised, then (x - mean) * istd (+ SpecAugment fill)
-// in place on that tile, which this CTA wrote earlier (L2-resident).  Whole CTA; sNorm: 160 floats.
-__device__ __forceinline__ void normalize_tile_in_kernel(const FbankLaunch& p, const TileDesc& t, float* sNorm) {
+// (x - mean) * istd (+ SpecAugment fill) in place over ALL rows of utterance `utt`, by the CTA that
+// completed the utterance's last tile.  The rows were written moments ago by this and other CTAs and
+// are read back from L2 (ld.cg: other SMs' data must not come from this SM's L1); four 16-byte loads
+// are kept in flight per thread.  sNorm: mean[80] | istd[80].
+__device__ __noinline__ void normalize_utterance_in_kernel(const FbankLaunch& p, int utt, int T, long long out_row,
+                                                              const float* sNorm, float mv) {
   const int tid = threadIdx.x;
-  if (tid == 0) {
-    while (ld_acquire(p.utt_flag + t.utt) != p.epoch) __nanosleep(32);
-  }
-  __syncthreads();
-  if (tid < kStatsPerTile) {
-    const float* src = tid < kMel ? p.norm_mean + (long long)t.utt * kMel + tid
-                                  : p.norm_istd + (long long)t.utt * kMel + (tid - kMel);
-    sNorm[tid] = __ldcg(src);
-  }
-  __syncthreads();
   const int n_masks = p.n_fmask + p.n_tmask;
-  const int* mk = (p.masks != nullptr) ? p.masks + (long long)t.utt * n_masks * 2 : nullptr;
-  const float mv = (mk != nullptr) ? __ldcg(p.utt_mask_value + t.utt) : 0.f;
-  float4* o4 = reinterpret_cast<float4*>(p.out + t.out_row0 * (long long)kMel);
+  const int* mk = (p.masks != nullptr) ? p.masks + (long long)utt * n_masks * 2 : nullptr;
+  float4* o4 = reinterpret_cast<float4*>(p.out + out_row * (long long)kMel);
   const float4* mu4 = reinterpret_cast<const float4*>(sNorm);
   const float4* is4 = reinterpret_cast<const float4*>(sNorm + kMel);
-  const int n4 = (int)t.nf * (kMel / 4);
-  for (int e = tid; e < n4; e += kThreads) {
-    const int f = e / (kMel / 4), c4 = e - f * (kMel / 4);
-    const float4 x = __ldcg(o4 + e);
-    const float4 mu = mu4[c4], is = is4[c4];
-    float4 y = make_float4((x.x - mu.x) * is.x, (x.y - mu.y) * is.y, (x.z - mu.z) * is.z, (x.w - mu.w) * is.w);
-    if (mk != nullptr) {
-      const int tt = t.frame0 + f;
-      bool trow = false;
-      for (int i = p.n_fmask; i < n_masks; ++i) trow |= (unsigned)(tt - mk[2 * i]) < (unsigned)mk[2 * i + 1];
-      bool m0 = trow, m1 = trow, m2 = trow, m3 = trow;
-      for (int i = 0; i < p.n_fmask; ++i) {
-        const int f0 = mk[2 * i];
-        const unsigned w = (unsigned)mk[2 * i + 1];
-        m0 |= (unsigned)(4 * c4 + 0 - f0) < w;
-        m1 |= (unsigned)(4 * c4 + 1 - f0) < w;
-        m2 |= (unsigned)(4 * c4 + 2 - f0) < w;
-        m3 |= (unsigned)(4 * c4 + 3 - f0) < w;
-      }
-      if (m0) y.x = mv;
-      if (m1) y.y = mv;
-      if (m2) y.z = mv;
-      if (m3) y.w = mv;
+  const int n4 = T * (kMel / 4);
+#ifndef JS2T_NORM_INFLIGHT
+#define JS2T_NORM_INFLIGHT 4
+#endif
+  constexpr int kInFlight = JS2T_NORM_INFLIGHT;
+#pragma unroll 1
+  for (int e0 = tid; e0 < n4; e0 += kInFlight * kThreads) {
+    float4 x[kInFlight];
+#pragma unroll
+    for (int j = 0; j < kInFlight; ++j) {
+      const int e = e0 + j * kThreads;
+      if (e < n4) x[j] = __ldcg(o4 + e);
     }
-    o4[e] = y;
+#pragma unroll
+    for (int j = 0; j < kInFlight; ++j) {
+      const int e = e0 + j * kThreads;
+      if (e >= n4) break;
+      const int f = e / (kMel / 4), c4 = e - f * (kMel / 4);
+      const float4 mu = mu4[c4], is = is4[c4];
+      float4 y = make_float4((x[j].x - mu.x) * is.x, (x[j].y - mu.y) * is.y, (x[j].z - mu.z) * is.z,
+                             (x[j].w - mu.w) * is.w);
+      if (mk != nullptr) {
+        bool trow = false;
+        for (int i = p.n_fmask; i < n_masks; ++i) trow |= (unsigned)(f - mk[2 * i]) < (unsigned)mk[2 * i + 1];
+        bool m0 = trow, m1 = trow, m2 = trow, m3 = trow;
+        for (int i = 0; i < p.n_fmask; ++i) {
+          const int f0 = mk[2 * i];
+          const unsigned w = (unsigned)mk[2 * i + 1];
+          m0 |= (unsigned)(4 * c4 + 0 - f0) < w;
+          m1 |= (unsigned)(4 * c4 + 1 - f0) < w;
+          m2 |= (unsigned)(4 * c4 + 2 - f0) < w;
+          m3 |= (unsigned)(4 * c4 + 3 - f0) < w;
+        }
+        if (m0) y.x = mv;
+        if (m1) y.y = mv;
+        if (m2) y.z = mv;
+        if (m3) y.w = mv;
+      }
+      __stcs(o4 + e, y);
+    }
   }
 }
 
+template <bool kFused>
 __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaunch p) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* sD = reinterpret_cast<float*>(smem + kOffD);
@@ -426,18 +466,31 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
 
   // ---- dynamic tile scheduler: tiles are handed out in order by one global counter.  The two CTAs
   // resident on an SM do not run at the same speed (the warp scheduler favours one of them by ~25 %),
-  // so a static round-robin split leaves the slower half of the grid as stragglers.  Each CTA holds
-  // the tile it computes (cur), the one whose PCM is being prefetched (next) and one claimed index
-  // further ahead whose descriptor load is in flight.
-  __shared__ int sClaim[2];
-  if (tid == 0) {
-    const int a = atomicAdd(p.sched, 2);
-    sClaim[0] = a;
-    sClaim[1] = a + 1;
-  }
+  // so a static round-robin split leaves the slower half of the grid as stragglers.  Everything about
+  // future tiles is fetched one full iteration before it is needed, so no latency is exposed:
+  //   cur        tile being computed
+  //   nxt        next tile: descriptor in registers, PCM in flight (bulk async copy)
+  //   sDesc      descriptor of the tile after that, landing in shared memory (cp.async issued at
+  //              the top of this iteration by thread 0, index in sClaim)
+  //   claim_next index one further ahead: thread 0's atomicAdd issued at the top of this iteration,
+  //              its return value is first needed at the top of the next one.
+  __shared__ int sClaim;
+  __shared__ __align__(16) TileDesc sDesc;
+#ifndef JS2T_SCHED_PIPE
+#define JS2T_SCHED_PIPE 1
+#endif
+#if JS2T_SCHED_PIPE
+  if (tid == 0) sClaim = atomicAdd(p.sched, 3);
   __syncthreads();
-  int tile = sClaim[0];
-  int next_tile = sClaim[1];
+  int tile = sClaim;
+  int next_tile = tile + 1;
+  int claim_cur = tile + 2, claim_next = 0;  // meaningful in thread 0 only
+#else
+  if (tid == 0) sClaim = atomicAdd(p.sched, 2);
+  __syncthreads();
+  int tile = sClaim;
+  int next_tile = tile + 1;
+#endif
   if (tile >= p.n_tiles) {  // more CTAs than tiles
     if (tid == 0 && atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
       p.sched[0] = 0;
@@ -449,18 +502,26 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
   TileDesc nxt = cur;
   if (next_tile < p.n_tiles) nxt = p.tiles[next_tile];
   unsigned parity = 0;
-  // fused CMVN: tiles this CTA has written and not yet normalised (their utterances' statistics may
-  // still be in flight in other CTAs)
-  constexpr int kMaxPend = 4;
-  __shared__ TileDesc sPend[kMaxPend];
-  __shared__ int sPendTile[kMaxPend];
-  int n_pend = 0;
-  __shared__ int sIsLast;
+  __shared__ int sIsLast;  // fused CMVN: this CTA completed the last tile of its utterance
   if (tid == 0 && cur.nf > 0 && !(cur.flags & 1)) prefetch_tile(p, cur, sRaw, sBar);
 
   while (true) {
-    __syncthreads();  // sClaim was read by everyone
-    if (tid == 0) sClaim[0] = atomicAdd(p.sched, 1);  // claim two ahead; consumed at the end of the iteration
+    __syncthreads();  // sClaim / sDesc were read by everyone
+#if JS2T_SCHED_PIPE
+    if (tid == 0) {
+      sClaim = claim_cur;
+      if (claim_cur < p.n_tiles) {
+        const unsigned dst = smem_u32(&sDesc);
+        const TileDesc* src = p.tiles + claim_cur;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"((const char*)src + 16)
+                     : "memory");
+      }
+      claim_next = atomicAdd(p.sched, 1);
+    }
+#else
+    if (tid == 0) sClaim = atomicAdd(p.sched, 1);  // claim two ahead; consumed at the end of the iteration
+#endif
     const bool has_next = next_tile < p.n_tiles;
     const bool next_tma = has_next && nxt.nf > 0 && !(nxt.flags & 1);
 
@@ -482,6 +543,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
         // int16 PCM, already in shared memory (bulk async copy issued one tile ago)
         mbar_wait(sBar, parity);
         parity ^= 1u;
+        if (!JS2T_SKIP(1)) {
         const int4* raw4 = reinterpret_cast<const int4*>(sRaw + 16);
         const short* raw = reinterpret_cast<const short*>(sRaw + 16);
         const bool at_start = cur.frame0 == 0;
@@ -509,6 +571,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
           reinterpret_cast<float4*>(sD)[2 * c] = d0;
           reinterpret_cast<float4*>(sD)[2 * c + 1] = d1;
           sPsum[c] = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+        }
         }
       } else {
         // float32 PCM in [-1, 1): straight from global memory (no staging buffer of that size)
@@ -560,7 +623,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
       __syncthreads();
 
       // ---- phase 2: two frames per half-warp (packed), four per warp -> power spectrum P[k][frame] ----
-      if (4 * warp < nf) {
+      if (4 * warp < nf && !JS2T_SKIP(2)) {
         const int half = lane >> 4;
         const int r = lane & 15;
         u64* exch = sExch + warp * kExchPerWarp + half * (16 * kExchStride);
@@ -584,12 +647,15 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
           v[13] = v[14] = v[15] = C2{0ull, 0ull};
         }
         // pass 1: DFT over n1 (lane = n2 = r), then twiddle by W_256^(n2*k1)
+        if (!JS2T_SKIP(16)) {
         fft16<true>(v);
 #pragma unroll
         for (int k1 = 1; k1 < 16; ++k1) {
           const float2 w = sTw256[k1 * 16 + r];
           v[k1] = cmul(v[k1], w.x, w.y);
         }
+        }
+        if (!JS2T_SKIP(32)) {
         // 16x16 transpose inside the half-warp, real parts then imaginary parts (keeps registers flat)
         __syncwarp();
 #pragma unroll
@@ -603,8 +669,9 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
         __syncwarp();
 #pragma unroll
         for (int n2 = 0; n2 < 16; ++n2) v[n2].im = exch[r * kExchStride + n2];
+        }
         // pass 2: DFT over n2 (lane = k1 = r): v[k2] = Z[r + 16 k2]
-        fft16<false>(v);
+        if (!JS2T_SKIP(16)) fft16<false>(v);
 
         // real-input split: bins k = r + 16 j and 256 - k from Z[k] and Z[256 - k] (partner lane)
         float* Pf = sP + fA;
@@ -642,7 +709,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
       {
         const float* Pl = sP + lane;
         float* orow = sOut + lane * kOutStride;
-        if (lane < nf) {
+        if (lane < nf && !JS2T_SKIP(4)) {
           switch (warp) {
 #define JS2T_GRP(g, m0, m1) \
   case g:                   \
@@ -660,7 +727,8 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
       // ---- phase 4: store.  Warp w owns rows 4w..4w+3; lane owns columns lane, lane+32, lane+64 -------
       {
         const bool c2ok = lane < kMel - 64;
-        if (p.epilogue == kEpiRaw) {
+        if (JS2T_SKIP(8)) {
+        } else if (p.epilogue == kEpiRaw) {
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -739,72 +807,51 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
       }
     }
     JS2T_STAMP(1)
-    if (!p.fused && p.dbg_times != nullptr && tid == 0) {
+    if (!kFused && p.dbg_times != nullptr && tid == 0) {
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
       p.dbg_times[(long long)tile * 4 + 2] = smid;
     }
-    if (p.fused) {
-      if (nf > 0) {
-        // publish this tile: raw rows + per-tile statistics are written; count it for its utterance
-        __syncthreads();
-        if (tid == 0) {
-          __threadfence();
-          sIsLast = (atomicAdd(p.utt_counter + cur.utt, 1) == cur.utt_tiles - 1);
-        }
-        __syncthreads();
-        if (sIsLast) {  // CTA-uniform
-          __threadfence();
-          finalize_utterance_in_kernel(p, cur, tile, sStat);
-          __threadfence();
-          __syncthreads();
-          if (tid == 0) {
-            p.utt_counter[cur.utt] = 0;  // ready for the next launch
-            st_release(p.utt_flag + cur.utt, p.epoch);
-          }
-        }
-      }
-      JS2T_STAMP(2)
-      if (nf > 0) {
-        if (tid == 0) {
-          sPend[n_pend] = cur;
-          sPendTile[n_pend] = tile;
-        }
-        ++n_pend;
-      }
-      // Normalise older tiles whose utterance lies entirely before the tile this CTA computes next:
-      // then no CTA that the utterance still depends on can itself be waiting for one of our tiles
-      // (deadlock-free), and with tiles handed out in order its statistics are normally complete.
+    if (kFused && nf > 0) {
+      // Fused utterance CMVN, "last arriver finishes the job": publish this tile (raw rows + per-tile
+      // statistics are written) and count it for its utterance.  Whichever CTA completes the
+      // utterance's last tile reduces the per-tile statistics in tile order (deterministic) and
+      // normalises (+ masks) the whole utterance while its rows are still L2-resident.  Nobody ever
+      // waits on another CTA; the dynamic tile scheduler absorbs the extra work of the finisher.
       __syncthreads();
-      while (n_pend > 0) {
-        const int first = sPendTile[0] - sPend[0].frame0 / kTileFrames;
-        const int last = first + sPend[0].utt_tiles - 1;
-        if (!(next_tile > last || !has_next || n_pend == kMaxPend)) break;
-        normalize_tile_in_kernel(p, sPend[0], sStat);
-        __syncthreads();
-        if (tid == 0) {
-          for (int i = 1; i < n_pend; ++i) {
-            sPend[i - 1] = sPend[i];
-            sPendTile[i - 1] = sPendTile[i];
-          }
-        }
-        --n_pend;
-        __syncthreads();
+      if (tid == 0) {
+        if (!JS2T_SKIP(128)) __threadfence();  // release: the barrier above ordered every thread's stores before this fence
+        sIsLast = (atomicAdd(p.utt_counter + cur.utt, 1) == cur.utt_tiles - 1);
+        __threadfence();  // acquire side for the finisher
+      }
+      __syncthreads();
+      JS2T_STAMP(2)
+      if (sIsLast) {  // CTA-uniform
+        finalize_utterance_in_kernel(p, cur, tile, sStat);
+        const float* sNorm = sStat + 2 * kStatsPerTile;
+        if (!JS2T_SKIP(64))
+          normalize_utterance_in_kernel(p, cur.utt, p.utts[cur.utt].n_frames, cur.out_row0 - cur.frame0, sNorm,
+                                        sNorm[2 * kMel]);
+        if (tid == 0) p.utt_counter[cur.utt] = 0;  // ready for the next launch
       }
       JS2T_STAMP(3)
     }
     if (!has_next) break;
-    __syncthreads();  // sD / sOut / sStat are rewritten by the next tile; sClaim[0] is visible
+#if JS2T_SCHED_PIPE
+    if (tid == 0) asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();  // sD / sOut / sStat are rewritten by the next tile; sClaim / sDesc are visible
     tile = next_tile;
     cur = nxt;
-    next_tile = sClaim[0];
-    if (next_tile < p.n_tiles) nxt = p.tiles[next_tile];  // first used after the next tile's staging phase
-  }
-  if (p.fused) {  // drain
-    for (int i = 0; i < n_pend; ++i) {
-      __syncthreads();
-      normalize_tile_in_kernel(p, sPend[i], sStat);
-    }
+    next_tile = sClaim;
+    if (next_tile < p.n_tiles) nxt = sDesc;
+    claim_cur = claim_next;
+#else
+    __syncthreads();  // sD / sOut / sStat are rewritten by the next tile; sClaim is visible
+    tile = next_tile;
+    cur = nxt;
+    next_tile = sClaim;
+    if (next_tile < p.n_tiles) nxt = p.tiles[next_tile];
+#endif
   }
   // the last CTA to leave re-arms the scheduler for the next launch
   if (tid == 0 && atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
@@ -1061,8 +1108,9 @@ int fbank_persistent_grid() {
     int dev = 0, n_sm = 0, occ = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(fbank_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fbank_tile_kernel, kThreads, kSmemBytes);
+    cudaFuncSetAttribute(fbank_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(fbank_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fbank_tile_kernel<true>, kThreads, kSmemBytes);
     if (occ < 1) occ = 1;
     g_fbank_grid = occ * n_sm;  // every CTA resident at once: one wave, persistent
   }
@@ -1073,14 +1121,10 @@ cudaError_t launch_fbank(const FbankLaunch& p, cudaStream_t s) {
   if (p.n_tiles <= 0) return cudaSuccess;
   const int full = fbank_persistent_grid();
   const int grid = p.n_tiles < full ? p.n_tiles : full;
-  if (p.fused) {
-    // CTAs wait on each other's statistics: co-residency must be guaranteed
-    FbankLaunch copy = p;
-    void* args[] = {&copy};
-    return cudaLaunchCooperativeKernel((const void*)fbank_tile_kernel, dim3(grid), dim3(kThreads), args,
-                                       (size_t)kSmemBytes, s);
-  }
-  fbank_tile_kernel<<<grid, kThreads, kSmemBytes, s>>>(p);
+  if (p.fused)
+    fbank_tile_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(p);
+  else
+    fbank_tile_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -338,3 +338,68 @@ def features_cmvn_specaug_ragged(
     torch.cuda.current_stream().synchronize()
     plan.close()
     return out, n_frames
+
+
+# ------------------------------------------------------------------------------------------
+# host-resident streaming: H2D, kernels and D2H of consecutive batches overlap
+# ------------------------------------------------------------------------------------------
+class HostPipeline:
+    """Host PCM in, host features out, for a stream of batches.
+
+    Each slot owns a device staging buffer, a device output and a pinned host output.  Three CUDA
+    streams (copy-in, compute, copy-out) are chained with events so that the H2D copy of batch
+    ``i+1``, the kernels of batch ``i`` and the D2H copy of batch ``i-1`` run concurrently — from
+    host memory the path is PCIe-bound, and PCIe is full duplex.
+
+    ``submit(packed, plan)`` returns the slot index; ``result(slot)`` blocks until that slot's
+    features are in pinned host memory and returns them as a (rows, 80) float32 tensor.
+    """
+
+    def __init__(self, n_slots: int, max_pcm_bytes: int, max_out_rows: int, device: Optional[int] = None):
+        _require_cuda()
+        self.device = torch.cuda.current_device() if device is None else device
+        dev = torch.device("cuda", self.device)
+        self.n_slots = n_slots
+        self.s_in, self.s_compute, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.stage = [torch.empty(max_pcm_bytes, dtype=torch.uint8, device=dev) for _ in range(n_slots)]
+        self.out = [torch.empty((max_out_rows, NUM_MEL), dtype=torch.float32, device=dev)
+                    for _ in range(n_slots)]
+        self.host_out = [torch.empty((max_out_rows, NUM_MEL), dtype=torch.float32, pin_memory=True)
+                         for _ in range(n_slots)]
+        self.ev_in = [torch.cuda.Event() for _ in range(n_slots)]
+        self.ev_compute = [torch.cuda.Event() for _ in range(n_slots)]
+        self.ev_out = [torch.cuda.Event() for _ in range(n_slots)]
+        self.rows = [0] * n_slots
+        self._next = 0
+        self._used = [False] * n_slots
+
+    def submit(self, packed: "PackedPCM", plan: "Plan") -> int:
+        j = self._next
+        self._next = (j + 1) % self.n_slots
+        assert packed.nbytes <= self.stage[j].numel() and plan.out_rows <= self.out[j].shape[0]
+        with torch.cuda.stream(self.s_in):
+            if self._used[j]:
+                self.s_in.wait_event(self.ev_compute[j])  # the slot's previous kernels have read the stage
+            self.stage[j][:packed.nbytes].copy_(packed.host[:packed.nbytes], non_blocking=True)
+            self.ev_in[j].record(self.s_in)
+        with torch.cuda.stream(self.s_compute):
+            self.s_compute.wait_event(self.ev_in[j])
+            if self._used[j]:
+                self.s_compute.wait_event(self.ev_out[j])  # the slot's previous output has left the device
+            plan.execute(self.stage[j], self.out[j])
+            self.ev_compute[j].record(self.s_compute)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_compute[j])
+            self.host_out[j][:plan.out_rows].copy_(self.out[j][:plan.out_rows], non_blocking=True)
+            self.ev_out[j].record(self.s_out)
+        self.rows[j] = plan.out_rows
+        self._used[j] = True
+        return j
+
+    def result(self, slot: int) -> torch.Tensor:
+        self.ev_out[slot].synchronize()
+        return self.host_out[slot][:self.rows[slot]]
+
+    def synchronize(self) -> None:
+        for s in (self.s_in, self.s_compute, self.s_out):
+            s.synchronize()

@@ -1,0 +1,86 @@
+# coding: utf-8
+"""
+CPU-side checks of the drop-in boundary: the in-tree shared library loads without a GPU, exports
+every symbol ``include/joeys2t_b200.h`` declares, its pure-host entry points answer, and the
+product path refuses to run (loudly, no fallback) when no CUDA device is usable.
+No compute call is made here.
+"""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from joeys2t_b200 import _lib
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = ROOT / "include" / "joeys2t_b200.h"
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if _lib.is_stale():
+        _lib.build()
+    return _lib.load()
+
+
+def header_symbols():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(js2t_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_list_agree():
+    assert header_symbols() == sorted(_lib.EXPORTED_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in header_symbols():
+        assert getattr(lib, name) is not None, name
+
+
+def test_version_and_frame_count(lib):
+    assert lib.js2t_version() == 100
+    # TA:63-67 (snip_edges): 1 + (n - 400) // 160, 0 below one window
+    for n, want in ((0, 0), (399, 0), (400, 1), (559, 1), (560, 2), (16000, 98), (240000, 1498)):
+        assert lib.js2t_num_frames(n) == want
+
+
+def test_argument_errors_set_last_error(lib):
+    assert lib.js2t_ctx_create(0, None) == _lib.ERR_INVALID
+    assert b"NULL" in lib.js2t_last_error()
+    assert lib.js2t_plan_set_cmvn(None, 1, 1, 1, 1) == _lib.ERR_INVALID
+    assert lib.js2t_fbank_execute(None, None, None, None) == _lib.ERR_INVALID
+    assert lib.js2t_plan_total_frames(None) == -1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device the C ABI reports JS2T_ERR_CUDA and the host API raises."""
+    h = ctypes.c_void_p()
+    assert lib.js2t_ctx_create(0, ctypes.byref(h)) == _lib.ERR_CUDA
+    from joeys2t_b200 import frontend, helpers_for_audio
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        frontend.get_context(0)
+    # the reference's error convention: failures surface as ValueError (helpers_for_audio.py:56-62)
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        helpers_for_audio.extract_fbank_features(torch.zeros(1, 16000), 16000)
+
+
+def test_product_path_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under joeys2t_b200/ may import it."""
+    for py in (ROOT / "joeys2t_b200").rglob("*.py"):
+        src = py.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), py
+
+
+def test_packed_pcm_alignment():
+    from joeys2t_b200 import frontend
+    waves = [np.arange(401, dtype=np.int16), np.zeros(403, np.float32), np.ones(999, np.int16)]
+    p = frontend.PackedPCM(waves)
+    assert (p.byte_off % 16 == 0).all() and p.is_f32.tolist() == [0, 1, 0]
+    hv = p.host.numpy()
+    assert np.array_equal(hv[:802].view(np.int16), waves[0])
+    o = int(p.byte_off[2])
+    assert np.array_equal(hv[o:o + 1998].view(np.int16), waves[2])
