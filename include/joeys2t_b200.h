@@ -136,10 +136,9 @@ int js2t_features_execute(js2t_plan* plan, const float* feats_dev, float* out_de
 int js2t_plan_enable_profiling(js2t_plan* plan, int n_slots);
 int js2t_plan_kernel_times_ms(js2t_plan* plan, float* ms_out, int n, int* n_written);
 
-/* Tuning / test switches.  "fused_cmvn" = 1 runs utterance CMVN inside the persistent fbank kernel
- * (the CTA that completes an utterance's last tile normalises it while it is L2-resident); the
- * default is the three-kernel path (fbank + per-tile statistics, finalize, apply), which is the
- * faster of the two on B200 today.  "debug_skip" only has an effect in -DJS2T_DBG=1 builds. */
+/* Tuning switches: "max_ctas" caps the persistent grid, "debug_times" records per-tile time stamps,
+ * "debug_skip" skips kernel phases in -DJS2T_DBG=1 builds.  "fused_cmvn" / "force_unfused" are
+ * accepted and ignored (the in-kernel CMVN variants of round 1 were slower and were removed). */
 int js2t_plan_set_option(js2t_plan* plan, const char* name, int value);
 /* With option "debug_times" = 1: per-tile %globaltimer stamps [n_tiles][4] (tile start, stored,
  * published, normalised-older-tile) of the last execute, copied to host memory (synchronous). */

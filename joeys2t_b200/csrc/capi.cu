@@ -64,7 +64,6 @@ struct js2t_plan {
   float* d_gmean = nullptr;
   float* d_gistd = nullptr;
   double* d_utt_stats = nullptr;
-  int* d_counter = nullptr;  // [n_utts] fused-CMVN tile counters (zero between launches)
   int* d_sched = nullptr;    // [2] tile scheduler counters of the persistent kernel (self-resetting)
   int max_utt_tiles = 0;
   int* d_masks = nullptr;
@@ -75,8 +74,8 @@ struct js2t_plan {
   float mask_value_const = 0.f;
   bool has_masks = false, global_stats_set = false, stats_valid = false;
   bool feature_input = false;  // rows of 80 floats instead of PCM (js2t_plan_create_features)
+  int grid_limit = 0;          // tuning only: option "max_ctas"
   int dbg_skip = 0;            // tuning only: phases of the fbank kernel to skip (results are wrong)
-  bool use_fused = false;      // option "fused_cmvn": utterance CMVN inside the persistent fbank kernel
   unsigned long long* d_dbg = nullptr;  // [n_tiles][4] debug time stamps (option "debug_times")
   // optional instrumentation: CUDA events around the fbank kernel of each execute (ring of slots)
   std::vector<cudaEvent_t> prof_ev;  // 2 per slot
@@ -284,7 +283,6 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
   const size_t o_mv = carve(sizeof(float) * n_utts);
   const size_t o_g = carve(sizeof(float) * 2 * kMel);
   const size_t o_ustats = carve(sizeof(double) * kStatsPerTile * n_utts);
-  const size_t o_counter = carve(sizeof(int) * n_utts);
   const size_t o_sched = carve(sizeof(int) * 2);
   cudaSetDevice(ctx->device);
   cudaError_t e = cudaMalloc(&p->d_ws, off);
@@ -302,9 +300,8 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
   p->d_gmean = reinterpret_cast<float*>(base + o_g);
   p->d_gistd = p->d_gmean + kMel;
   p->d_utt_stats = reinterpret_cast<double*>(base + o_ustats);
-  p->d_counter = reinterpret_cast<int*>(base + o_counter);
   p->d_sched = reinterpret_cast<int*>(base + o_sched);
-  e = cudaMemset(p->d_counter, 0, (o_sched - o_counter) + sizeof(int) * 2);
+  e = cudaMemset(p->d_sched, 0, sizeof(int) * 2);
   if (e == cudaSuccess) e = cudaMemcpy(p->d_utts, p->h_utts.data(), sizeof(UttDesc) * n_utts, cudaMemcpyHostToDevice);
   if (e == cudaSuccess)
     e = cudaMemcpy(p->d_tiles, tiles.data(), sizeof(TileDesc) * tiles.size(), cudaMemcpyHostToDevice);
@@ -493,6 +490,8 @@ static int run_pipeline(js2t_plan* plan, const void* in_dev, float* out_dev, cud
   f.pad_value = plan->pad_value;
   f.epilogue = kEpiRaw;
   f.dbg_skip = plan->dbg_skip;
+  f.grid_limit = plan->grid_limit;
+  f.dbg_times = plan->d_dbg;
 
   // the dominant kernel, optionally bracketed by profiling events on the launching stream
   auto launch_main = [&](const FbankLaunch& fl) -> cudaError_t {
@@ -515,7 +514,8 @@ static int run_pipeline(js2t_plan* plan, const void* in_dev, float* out_dev, cud
   // (2) global CMVN with known statistics and no data-dependent fill value: normalise (+ mask) in
   //     the fbank epilogue, still one pass
   const bool mean_fill = masks && plan->mask_value_mode == JS2T_MASK_VALUE_MEAN;
-  if (from_pcm && mode == JS2T_CMVN_GLOBAL && !mean_fill && plan->before) {
+  if (from_pcm && mode == JS2T_CMVN_GLOBAL && !mean_fill && plan->before &&
+      (!masks || plan->n_fmask + plan->n_tmask <= 16)) {
     f.epilogue = kEpiNormKnown;
     f.g_mean = plan->d_gmean;
     f.g_istd = plan->d_gistd;
@@ -530,30 +530,9 @@ static int run_pipeline(js2t_plan* plan, const void* in_dev, float* out_dev, cud
     plan->stats_valid = false;
     return JS2T_OK;
   }
-  // (3a) utterance CMVN (before SpecAugment): statistics, finalisation and normalisation all inside
-  //      the persistent fbank kernel (the CTA that completes an utterance's last tile finishes it)
   f.tile_stats = plan->d_tile_stats;
-  if (from_pcm && mode == JS2T_CMVN_UTTERANCE && (plan->before || !masks) && plan->use_fused) {
-    f.fused = 1;
-    f.norm_means = plan->norm_means;
-    f.norm_vars = plan->norm_vars;
-    f.mask_value_mode = plan->mask_value_mode;
-    f.mask_value_const = plan->mask_value_const;
-    f.masks = masks ? plan->d_masks : nullptr;
-    f.n_fmask = masks ? plan->n_fmask : 0;
-    f.n_tmask = masks ? plan->n_tmask : 0;
-    f.utt_counter = plan->d_counter;
-    f.norm_mean = plan->d_mean;
-    f.norm_istd = plan->d_istd;
-    f.utt_mask_value = plan->d_mask_value;
-    f.stats_out = plan->d_utt_stats;
-    f.dbg_times = plan->d_dbg;
-    JS2T_CUDA(launch_main(f));
-    plan->stats_valid = true;
-    return JS2T_OK;
-  }
   f.dbg_times = plan->d_dbg;
-  // (3b) raw log-mel + per-tile statistics -> per-utterance finalize -> in-place apply
+  // (3) raw log-mel + per-tile statistics -> per-utterance finalize -> in-place apply
   JS2T_CUDA(launch_main(f));
   const bool shared = (mode == JS2T_CMVN_GLOBAL);
   FinalizeLaunch z = make_finalize(plan, out_dev, shared);
@@ -604,12 +583,10 @@ int js2t_plan_kernel_times_ms(js2t_plan* plan, float* ms_out, int n, int* n_writ
 
 int js2t_plan_set_option(js2t_plan* plan, const char* name, int value) {
   if (plan == nullptr || name == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
-  if (strcmp(name, "fused_cmvn") == 0) {
-    plan->use_fused = value != 0;
-    return JS2T_OK;
-  }
-  if (strcmp(name, "force_unfused") == 0) {  // older spelling of fused_cmvn = !value
-    plan->use_fused = value == 0;
+  if (strcmp(name, "fused_cmvn") == 0 || strcmp(name, "force_unfused") == 0)
+    return JS2T_OK;  // accepted for compatibility: the in-kernel variant was removed
+  if (strcmp(name, "max_ctas") == 0) {
+    plan->grid_limit = value;
     return JS2T_OK;
   }
   if (strcmp(name, "debug_skip") == 0) {

@@ -325,119 +325,39 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 #define JS2T_STAMP(slot)                                                                     \
   if (p.dbg_times != nullptr && tid == 0) p.dbg_times[(long long)tile * 4 + (slot)] = globaltimer_ns();
 
-// Executed by the whole CTA that published the last tile of utterance `utt`: per-bin sums over the
-// utterance's tiles in tile order (deterministic), then mean / inverse std (data_augmentation.py:96-109)
-// and the SpecAugment fill value (mean of the CMVN output, :45-46).
-// fixed-order (tile 0, 1, 2, ...) fp64 sum of one statistics column over n tiles, loads batched by 8
+// fixed-order (tile 0, 1, 2, ...) fp64 sum of one statistics column over n tiles; 16 independent
+// loads in flight per thread (the kernel is pure L2 latency)
 __device__ __forceinline__ double sum_tile_column(const float* ts, int n) {
   double acc = 0.0;
   int i = 0;
-  for (; i + 8 <= n; i += 8) {
+  for (; i + 16 <= n; i += 16) {
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __ldcg(ts + (long long)(i + j) * kStatsPerTile);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc += (double)v[j];
+  }
+  if (i + 8 <= n) {
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = __ldcg(ts + (long long)(i + j) * kStatsPerTile);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc += (double)v[j];
+    i += 8;
   }
   for (; i < n; ++i) acc += (double)__ldcg(ts + (long long)i * kStatsPerTile);
   return acc;
 }
 
-// Leaves mean[80] | istd[80] | fill value in sNorm (= sScratch + 160 doubles) for the normalisation.
-__device__ __noinline__ void finalize_utterance_in_kernel(const FbankLaunch& p, const TileDesc& t, int tile, float* sScratch) {
-  const int tid = threadIdx.x;
-  float* sNorm = sScratch + 2 * kStatsPerTile;
-  const int first_tile = tile - t.frame0 / kTileFrames;
-  const int T = p.utts[t.utt].n_frames;
-  double* sRed = reinterpret_cast<double*>(sScratch);  // [160] column sums, then [80] column means
-  if (tid < kStatsPerTile) {
-    const double acc = sum_tile_column(p.tile_stats + (long long)first_tile * kStatsPerTile + tid, t.utt_tiles);
-    sRed[tid] = acc;
-    if (p.stats_out != nullptr) p.stats_out[(long long)t.utt * kStatsPerTile + tid] = acc;
-  }
-  __syncthreads();
-  double col = 0.0;
-  if (tid < kMel) {
-    const double S = sRed[tid], Q = sRed[kMel + tid];
-    const double mu = S / T;
-    double mean = 0.0, istd = 1.0;
-    if (p.norm_means) mean = (double)(float)mu;
-    if (p.norm_vars) istd = 1.0 / sqrt(fmax(Q / T - mu * mu, 1e-10));
-    p.norm_mean[(long long)t.utt * kMel + tid] = (float)mean;
-    p.norm_istd[(long long)t.utt * kMel + tid] = (float)istd;
-    sNorm[tid] = (float)mean;
-    sNorm[kMel + tid] = (float)istd;
-    col = (mu - mean) * istd;  // column mean of the normalised utterance
-  }
-  __syncthreads();
-  if (tid < kMel) sRed[tid] = col;
-  __syncthreads();
-  if (tid == 0) {
-    double acc = 0.0;
-    for (int i = 0; i < kMel; ++i) acc += sRed[i];
-    const float mv = (p.mask_value_mode == 1) ? p.mask_value_const : (float)(acc / kMel);
-    p.utt_mask_value[t.utt] = mv;
-    sNorm[2 * kMel] = mv;
-  }
-  __syncthreads();
-}
+// kMode: 0 = raw log-mel (+ per-tile statistics),
+//        2 = statistics known up front (global CMVN): normalise + SpecAugment fill in the epilogue
+// (mode 1, per-utterance finalisation inside this kernel by the CTA that completes an utterance's
+//  last tile, was built and measured in round 1 and removed: any per-tile fence + atomic signalling
+//  costs more than the separate 12 us finalize kernel — DESIGN.md 3.3, profiles/r1c_*)
+constexpr int kModeRaw = 0, kModeNormKnown = 2;
+constexpr int kMaxEpilogueMasks = 16;
 
-// (x - mean) * istd (+ SpecAugment fill) in place over ALL rows of utterance `utt`, by the CTA that
-// completed the utterance's last tile.  The rows were written moments ago by this and other CTAs and
-// are read back from L2 (ld.cg: other SMs' data must not come from this SM's L1); four 16-byte loads
-// are kept in flight per thread.  sNorm: mean[80] | istd[80].
-__device__ __noinline__ void normalize_utterance_in_kernel(const FbankLaunch& p, int utt, int T, long long out_row,
-                                                              const float* sNorm, float mv) {
-  const int tid = threadIdx.x;
-  const int n_masks = p.n_fmask + p.n_tmask;
-  const int* mk = (p.masks != nullptr) ? p.masks + (long long)utt * n_masks * 2 : nullptr;
-  float4* o4 = reinterpret_cast<float4*>(p.out + out_row * (long long)kMel);
-  const float4* mu4 = reinterpret_cast<const float4*>(sNorm);
-  const float4* is4 = reinterpret_cast<const float4*>(sNorm + kMel);
-  const int n4 = T * (kMel / 4);
-#ifndef JS2T_NORM_INFLIGHT
-#define JS2T_NORM_INFLIGHT 4
-#endif
-  constexpr int kInFlight = JS2T_NORM_INFLIGHT;
-#pragma unroll 1
-  for (int e0 = tid; e0 < n4; e0 += kInFlight * kThreads) {
-    float4 x[kInFlight];
-#pragma unroll
-    for (int j = 0; j < kInFlight; ++j) {
-      const int e = e0 + j * kThreads;
-      if (e < n4) x[j] = __ldcg(o4 + e);
-    }
-#pragma unroll
-    for (int j = 0; j < kInFlight; ++j) {
-      const int e = e0 + j * kThreads;
-      if (e >= n4) break;
-      const int f = e / (kMel / 4), c4 = e - f * (kMel / 4);
-      const float4 mu = mu4[c4], is = is4[c4];
-      float4 y = make_float4((x[j].x - mu.x) * is.x, (x[j].y - mu.y) * is.y, (x[j].z - mu.z) * is.z,
-                             (x[j].w - mu.w) * is.w);
-      if (mk != nullptr) {
-        bool trow = false;
-        for (int i = p.n_fmask; i < n_masks; ++i) trow |= (unsigned)(f - mk[2 * i]) < (unsigned)mk[2 * i + 1];
-        bool m0 = trow, m1 = trow, m2 = trow, m3 = trow;
-        for (int i = 0; i < p.n_fmask; ++i) {
-          const int f0 = mk[2 * i];
-          const unsigned w = (unsigned)mk[2 * i + 1];
-          m0 |= (unsigned)(4 * c4 + 0 - f0) < w;
-          m1 |= (unsigned)(4 * c4 + 1 - f0) < w;
-          m2 |= (unsigned)(4 * c4 + 2 - f0) < w;
-          m3 |= (unsigned)(4 * c4 + 3 - f0) < w;
-        }
-        if (m0) y.x = mv;
-        if (m1) y.y = mv;
-        if (m2) y.z = mv;
-        if (m3) y.w = mv;
-      }
-      __stcs(o4 + e, y);
-    }
-  }
-}
-
-template <bool kFused>
+template <int kMode>
 __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaunch p) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* sD = reinterpret_cast<float*>(smem + kOffD);
@@ -462,6 +382,11 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
   sTw256[tid] = p.tab.tw256[tid];
   if (tid < 136) sTw512[tid] = p.tab.tw512[tid];
   if (tid == 0) mbar_init(sBar, 1);
+  __shared__ float sGN[kMode == kModeNormKnown ? 2 * kMel : 1];                    // global mean | 1/std
+  __shared__ int sMaskTab[kMode == kModeNormKnown ? 2 * kMaxEpilogueMasks : 1];  // this tile's utterance
+  __shared__ float sMaskVal;
+  __shared__ unsigned sTileMask[4];  // per tile: masked rows | masked columns (3 words), see the epilogue
+  if (kMode == kModeNormKnown && tid < 2 * kMel) sGN[tid] = tid < kMel ? p.g_mean[tid] : p.g_istd[tid - kMel];
   __syncthreads();
 
   // ---- dynamic tile scheduler: tiles are handed out in order by one global counter.  The two CTAs
@@ -502,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
   TileDesc nxt = cur;
   if (next_tile < p.n_tiles) nxt = p.tiles[next_tile];
   unsigned parity = 0;
-  __shared__ int sIsLast;  // fused CMVN: this CTA completed the last tile of its utterance
+
   if (tid == 0 && cur.nf > 0 && !(cur.flags & 1)) prefetch_tile(p, cur, sRaw, sBar);
 
   while (true) {
@@ -524,6 +449,20 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
 #endif
     const bool has_next = next_tile < p.n_tiles;
     const bool next_tma = has_next && nxt.nf > 0 && !(nxt.flags & 1);
+    if (kMode == kModeNormKnown && p.masks != nullptr) {
+      // this utterance's mask table and fill value -> shared memory (read two barriers later)
+      // (cp.async: fire and forget now, waited for just before the barrier in front of the epilogue,
+      // so the global-memory latency is hidden behind the FFT and costs no registers)
+      const int n2 = 2 * (p.n_fmask + p.n_tmask);
+      if (tid < n2)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&sMaskTab[tid])),
+                     "l"(p.masks + (long long)cur.utt * n2 + tid)
+                     : "memory");
+      if (tid == 32)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&sMaskVal)),
+                     "l"(p.mask_value + cur.utt)
+                     : "memory");
+    }
 
     JS2T_STAMP(0)
     const int nf = cur.nf;      // valid frames in this tile
@@ -722,13 +661,43 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
           }
         }
       }
+      if (kMode == kModeNormKnown && tid <= 32) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        if (warp == 0) {  // turn this utterance's mask table into row / column bit masks of the tile
+          __syncwarp();
+          bool trow = false, c0 = false, c1 = false, c2 = false;
+          if (p.masks != nullptr) {
+            const int t = cur.frame0 + lane;
+            for (int i = 0; i < p.n_fmask; ++i) {
+              const int f0 = sMaskTab[2 * i];
+              const unsigned w = (unsigned)sMaskTab[2 * i + 1];
+              c0 |= (unsigned)(lane - f0) < w;
+              c1 |= (unsigned)(lane + 32 - f0) < w;
+              c2 |= (unsigned)(lane + 64 - f0) < w;
+            }
+            for (int i = p.n_fmask; i < p.n_fmask + p.n_tmask; ++i)
+              trow |= (unsigned)(t - sMaskTab[2 * i]) < (unsigned)sMaskTab[2 * i + 1];
+          }
+          const unsigned b0 = __ballot_sync(0xffffffffu, trow), b1 = __ballot_sync(0xffffffffu, c0),
+                         b2 = __ballot_sync(0xffffffffu, c1), b3 = __ballot_sync(0xffffffffu, c2);
+          if (lane == 0) {
+            sTileMask[0] = b0;
+            sTileMask[1] = b1;
+            sTileMask[2] = b2;
+            sTileMask[3] = b3;
+          }
+        }
+      }
       __syncthreads();
 
       // ---- phase 4: store.  Warp w owns rows 4w..4w+3; lane owns columns lane, lane+32, lane+64 -------
       {
         const bool c2ok = lane < kMel - 64;
         if (JS2T_SKIP(8)) {
-        } else if (p.epilogue == kEpiRaw) {
+#ifndef JS2T_TEST_EPI
+#define JS2T_TEST_EPI 0
+#endif
+        } else if (kMode != kModeNormKnown || JS2T_TEST_EPI == 1) {
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -764,77 +733,41 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
               p.tile_stats[(long long)tile * kStatsPerTile + tid] = acc;
             }
           }
-        } else {  // kEpiNormKnown: (x - mean) * istd and SpecAugment fill at store
-          const int* mk = p.masks ? p.masks + (long long)cur.utt * (p.n_fmask + p.n_tmask) * 2 : nullptr;
-          const float mv = p.mask_value ? p.mask_value[cur.utt] : 0.f;
-          float mu[3], is[3];
-          bool cm[3] = {false, false, false};
+        } else if (kMode == kModeNormKnown) {  // (x - mean) * istd and SpecAugment fill at store
+          // sTileMask (written by warp 0 before the barrier): bit f of [0] = row f is inside a time
+          // mask; bit l of [1 + c] = column l + 32 c is inside a frequency mask
+          const float mv = sMaskVal;
+          const unsigned rowm = sTileMask[0];
+          float x[12];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float* src = sOut + (4 * warp + i) * kOutStride + lane;
+            x[3 * i] = src[0];
+            x[3 * i + 1] = src[32];
+            x[3 * i + 2] = src[64];  // lanes >= 16: inside the padded row, never stored
+          }
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             const int m = min(lane + 32 * c, kMel - 1);
-            mu[c] = p.g_mean[m];
-            is[c] = p.g_istd[m];
-            if (mk != nullptr)
-              for (int i = 0; i < p.n_fmask; ++i) cm[c] |= (unsigned)(m - mk[2 * i]) < (unsigned)mk[2 * i + 1];
-          }
-#pragma unroll 1
-          for (int i = 0; i < 4; ++i) {
-            const int f = 4 * warp + i;
-            if (f < rows) {
-              const bool valid = f < nf;
-              bool trow = false;
-              if (mk != nullptr) {
-                const int t = cur.frame0 + f;
-                for (int k = p.n_fmask; k < p.n_fmask + p.n_tmask; ++k)
-                  trow |= (unsigned)(t - mk[2 * k]) < (unsigned)mk[2 * k + 1];
-              }
-              const float* src = sOut + f * kOutStride + lane;
-              float* dst = out_tile + f * kMel + lane;
+            const float mu = sGN[m], is = sGN[kMel + m];
+            const bool colm = (sTileMask[1 + c] >> lane) & 1u;
 #pragma unroll
-              for (int c = 0; c < 3; ++c) {
-                if (c < 2 || c2ok) {
-                  float y = p.pad_value;
-                  if (valid) {
-                    y = (src[32 * c] - mu[c]) * is[c];
-                    if (trow || cm[c]) y = mv;
-                  }
-                  dst[32 * c] = y;
-                }
-              }
+            for (int i = 0; i < 4; ++i) {
+              const int f = 4 * warp + i;
+              float y = (x[3 * i + c] - mu) * is;
+              if (colm || ((rowm >> f) & 1u)) y = mv;
+              if (f >= nf) y = p.pad_value;
+              if (f < rows && (c < 2 || c2ok)) out_tile[f * kMel + lane + 32 * c] = y;
             }
           }
         }
       }
     }
     JS2T_STAMP(1)
-    if (!kFused && p.dbg_times != nullptr && tid == 0) {
+    if (p.dbg_times != nullptr && tid == 0) {
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
       p.dbg_times[(long long)tile * 4 + 2] = smid;
-    }
-    if (kFused && nf > 0) {
-      // Fused utterance CMVN, "last arriver finishes the job": publish this tile (raw rows + per-tile
-      // statistics are written) and count it for its utterance.  Whichever CTA completes the
-      // utterance's last tile reduces the per-tile statistics in tile order (deterministic) and
-      // normalises (+ masks) the whole utterance while its rows are still L2-resident.  Nobody ever
-      // waits on another CTA; the dynamic tile scheduler absorbs the extra work of the finisher.
-      __syncthreads();
-      if (tid == 0) {
-        if (!JS2T_SKIP(128)) __threadfence();  // release: the barrier above ordered every thread's stores before this fence
-        sIsLast = (atomicAdd(p.utt_counter + cur.utt, 1) == cur.utt_tiles - 1);
-        __threadfence();  // acquire side for the finisher
-      }
-      __syncthreads();
-      JS2T_STAMP(2)
-      if (sIsLast) {  // CTA-uniform
-        finalize_utterance_in_kernel(p, cur, tile, sStat);
-        const float* sNorm = sStat + 2 * kStatsPerTile;
-        if (!JS2T_SKIP(64))
-          normalize_utterance_in_kernel(p, cur.utt, p.utts[cur.utt].n_frames, cur.out_row0 - cur.frame0, sNorm,
-                                        sNorm[2 * kMel]);
-        if (tid == 0) p.utt_counter[cur.utt] = 0;  // ready for the next launch
-      }
-      JS2T_STAMP(3)
     }
     if (!has_next) break;
 #if JS2T_SCHED_PIPE
@@ -891,24 +824,28 @@ __global__ void __launch_bounds__(kThreads) feature_tile_kernel(const FbankLaunc
 //  Kernel F: per-utterance statistics -> mean / inverse std / SpecAugment fill value
 //  (joeynmt/data_augmentation.py:96-109 CMVN; :43-46 mask value; tokenizers.py:488-493 order)
 // =====================================================================================================
-__global__ void __launch_bounds__(128) finalize_utt_kernel(const FinalizeLaunch p) {
+constexpr int kFinalizeThreads = 192;
+__global__ void __launch_bounds__(kFinalizeThreads) finalize_utt_kernel(const FinalizeLaunch p) {
   const int u = blockIdx.x;
-  const int b = threadIdx.x;  // mel bin
+  const int b = threadIdx.x;  // mel bin (threads >= 80 only help with the column sums)
   const UttDesc ud = p.utts[u];
   const int T = ud.n_frames;
   const int n_tiles = (T + kTileFrames - 1) / kTileFrames;
   __shared__ double s_red[kMel];
+  __shared__ double s_col[kStatsPerTile];
   __shared__ float s_mv;
 
+  if (b < kStatsPerTile) {  // one thread per statistics column: sums and sums of squares side by side
+    const float* ts = p.tile_stats + (long long)ud.tile_start * kStatsPerTile;
+    const double acc = sum_tile_column(ts + b, n_tiles);  // fixed order: deterministic
+    s_col[b] = acc;
+    if (p.stats_out != nullptr) p.stats_out[(long long)u * kStatsPerTile + b] = acc;
+  }
+  __syncthreads();
   double S = 0.0, Q = 0.0;
   if (b < kMel) {
-    const float* ts = p.tile_stats + (long long)ud.tile_start * kStatsPerTile;
-    S = sum_tile_column(ts + b, n_tiles);  // fixed order: deterministic
-    Q = sum_tile_column(ts + kMel + b, n_tiles);
-    if (p.stats_out != nullptr) {
-      p.stats_out[(long long)u * kStatsPerTile + b] = S;
-      p.stats_out[(long long)u * kStatsPerTile + kMel + b] = Q;
-    }
+    S = s_col[b];
+    Q = s_col[kMel + b];
   }
   const int n_masks = p.n_fmask + p.n_tmask;
   const int* mk = (p.masks != nullptr) ? p.masks + (long long)u * n_masks * 2 : nullptr;
@@ -998,57 +935,108 @@ __global__ void __launch_bounds__(128) finalize_utt_kernel(const FinalizeLaunch 
 // =====================================================================================================
 //  Kernel C: in-place CMVN + SpecAugment fill (+ padding rows of the padded layout)
 // =====================================================================================================
-__global__ void __launch_bounds__(kThreads) apply_kernel(const ApplyLaunch p) {
-  const TileDesc td = p.tiles[blockIdx.x];
-  const int frame0 = td.frame0;
-  const int nf = td.nf;
-  const int rows = td.rows;
-  float4* __restrict__ o4 = reinterpret_cast<float4*>(p.out + td.out_row0 * (long long)kMel);
-  const long long so = p.shared_stats ? 0 : (long long)td.utt * kMel;
-  const float4* mean4 = reinterpret_cast<const float4*>(p.mean + so);
-  const float4* istd4 = reinterpret_cast<const float4*>(p.istd + so);
-  const int n_masks = p.n_fmask + p.n_tmask;
-  const int* mk = (p.masks != nullptr) ? p.masks + (long long)td.utt * n_masks * 2 : nullptr;
-  const float mv = (p.mask_value != nullptr) ? p.mask_value[td.utt] : 0.f;
+// Each CTA normalises kApplyTiles consecutive tiles.  The kernel is a pure stream (read 320 B, write
+// 320 B per frame, mostly L2 hits right after the fbank kernel) and therefore bound by the bytes in
+// flight per SM: every thread issues all of its 16-byte loads (up to 3 per tile) before the first use.
+#ifndef JS2T_APPLY_TILES
+#define JS2T_APPLY_TILES 1
+#endif
+constexpr int kApplyTiles = JS2T_APPLY_TILES;
+constexpr int kApplyVec = (kTileFrames * (kMel / 4) + kThreads - 1) / kThreads;  // float4 per thread per tile = 3
 
-  for (int e = threadIdx.x; e < rows * (kMel / 4); e += kThreads) {
-    const int f = e / (kMel / 4), c4 = e - f * (kMel / 4);
-    float4 y;
-    if (f < nf) {
-      float4 x = o4[e];
-      const float4 mu = mean4[c4], is = istd4[c4];
-      bool m0 = false, m1 = false, m2 = false, m3 = false;
-      if (mk != nullptr) {
-        const int t = frame0 + f;
-        bool trow = false;
-        for (int i = p.n_fmask; i < n_masks; ++i) trow |= (unsigned)(t - mk[2 * i]) < (unsigned)mk[2 * i + 1];
-        m0 = m1 = m2 = m3 = trow;
-        for (int i = 0; i < p.n_fmask; ++i) {
-          const int f0 = mk[2 * i];
-          const unsigned w = (unsigned)mk[2 * i + 1];
-          m0 |= (unsigned)(4 * c4 + 0 - f0) < w;
-          m1 |= (unsigned)(4 * c4 + 1 - f0) < w;
-          m2 |= (unsigned)(4 * c4 + 2 - f0) < w;
-          m3 |= (unsigned)(4 * c4 + 3 - f0) < w;
-        }
+__global__ void __launch_bounds__(kThreads) apply_kernel(const ApplyLaunch p) {
+  const int tile0 = blockIdx.x * kApplyTiles;
+  const int n_masks = p.n_fmask + p.n_tmask;
+  __shared__ unsigned sMask[kApplyTiles][4];  // per tile: masked rows | masked columns (3 words)
+
+  // the utterance's mask table -> bit masks of each tile (warp j handles tile j)
+  if (threadIdx.x < 32 * kApplyTiles) {
+    const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    bool trow = false, c0 = false, c1 = false, c2 = false;
+    if (p.masks != nullptr && tile0 + j < p.n_tiles) {
+      const TileDesc td = p.tiles[tile0 + j];
+      const int* mk = p.masks + (long long)td.utt * n_masks * 2;
+      for (int i = 0; i < p.n_fmask; ++i) {
+        const int f0 = mk[2 * i];
+        const unsigned w = (unsigned)mk[2 * i + 1];
+        c0 |= (unsigned)(lane - f0) < w;
+        c1 |= (unsigned)(lane + 32 - f0) < w;
+        c2 |= (unsigned)(lane + 64 - f0) < w;
       }
-      if (p.cmvn_after) {  // SpecAugment saw the raw log-mel; CMVN normalises the filled cells too
-        if (m0) x.x = mv;
-        if (m1) x.y = mv;
-        if (m2) x.z = mv;
-        if (m3) x.w = mv;
-      }
-      y = make_float4((x.x - mu.x) * is.x, (x.y - mu.y) * is.y, (x.z - mu.z) * is.z, (x.w - mu.w) * is.w);
-      if (!p.cmvn_after) {
-        if (m0) y.x = mv;
-        if (m1) y.y = mv;
-        if (m2) y.z = mv;
-        if (m3) y.w = mv;
-      }
-    } else {
-      y = make_float4(p.pad_value, p.pad_value, p.pad_value, p.pad_value);
+      for (int i = p.n_fmask; i < n_masks; ++i)
+        trow |= (unsigned)(td.frame0 + lane - mk[2 * i]) < (unsigned)mk[2 * i + 1];
     }
-    o4[e] = y;
+    const unsigned b0 = __ballot_sync(0xffffffffu, trow), b1 = __ballot_sync(0xffffffffu, c0),
+                   b2 = __ballot_sync(0xffffffffu, c1), b3 = __ballot_sync(0xffffffffu, c2);
+    if (lane == 0) {
+      sMask[j][0] = b0;
+      sMask[j][1] = b1;
+      sMask[j][2] = b2;
+      sMask[j][3] = b3;
+    }
+  }
+
+  // issue every load of this thread first
+  float4 x[kApplyTiles][kApplyVec];
+  int nfv[kApplyTiles], rowsv[kApplyTiles], uttv[kApplyTiles];
+  float4* o4v[kApplyTiles];
+#pragma unroll
+  for (int j = 0; j < kApplyTiles; ++j) {
+    nfv[j] = rowsv[j] = uttv[j] = 0;
+    o4v[j] = nullptr;
+    if (tile0 + j < p.n_tiles) {
+      const TileDesc td = p.tiles[tile0 + j];
+      nfv[j] = td.nf;
+      rowsv[j] = td.rows;
+      uttv[j] = td.utt;
+      o4v[j] = reinterpret_cast<float4*>(p.out + td.out_row0 * (long long)kMel);
+#pragma unroll
+      for (int v = 0; v < kApplyVec; ++v) {
+        const int e = threadIdx.x + v * kThreads;
+        if (e < nfv[j] * (kMel / 4)) x[j][v] = o4v[j][e];
+      }
+    }
+  }
+  __syncthreads();
+
+#pragma unroll
+  for (int j = 0; j < kApplyTiles; ++j) {
+    if (o4v[j] == nullptr) continue;
+    const long long so = p.shared_stats ? 0 : (long long)uttv[j] * kMel;
+    const float4* mean4 = reinterpret_cast<const float4*>(p.mean + so);
+    const float4* istd4 = reinterpret_cast<const float4*>(p.istd + so);
+    const float mv = (p.mask_value != nullptr) ? p.mask_value[uttv[j]] : 0.f;
+    const unsigned rowm = sMask[j][0];
+#pragma unroll
+    for (int v = 0; v < kApplyVec; ++v) {
+      const int e = threadIdx.x + v * kThreads;
+      if (e >= rowsv[j] * (kMel / 4)) continue;
+      const int f = e / (kMel / 4), c4 = e - f * (kMel / 4);
+      float4 y;
+      if (f < nfv[j]) {
+        float4 xx = x[j][v];
+        const float4 mu = mean4[c4], is = istd4[c4];
+        // four column bits of this float4 (never straddle a word) | the row bit
+        unsigned m = (sMask[j][1 + (c4 >> 3)] >> ((4 * c4) & 31)) & 0xfu;
+        if ((rowm >> f) & 1u) m = 0xfu;
+        if (p.cmvn_after) {  // SpecAugment saw the raw log-mel; CMVN normalises the filled cells too
+          if (m & 1u) xx.x = mv;
+          if (m & 2u) xx.y = mv;
+          if (m & 4u) xx.z = mv;
+          if (m & 8u) xx.w = mv;
+        }
+        y = make_float4((xx.x - mu.x) * is.x, (xx.y - mu.y) * is.y, (xx.z - mu.z) * is.z, (xx.w - mu.w) * is.w);
+        if (!p.cmvn_after) {
+          if (m & 1u) y.x = mv;
+          if (m & 2u) y.y = mv;
+          if (m & 4u) y.z = mv;
+          if (m & 8u) y.w = mv;
+        }
+      } else {
+        y = make_float4(p.pad_value, p.pad_value, p.pad_value, p.pad_value);
+      }
+      o4v[j][e] = y;
+    }
   }
 }
 
@@ -1108,9 +1096,9 @@ int fbank_persistent_grid() {
     int dev = 0, n_sm = 0, occ = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(fbank_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    cudaFuncSetAttribute(fbank_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fbank_tile_kernel<true>, kThreads, kSmemBytes);
+    cudaFuncSetAttribute(fbank_tile_kernel<kModeRaw>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(fbank_tile_kernel<kModeNormKnown>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fbank_tile_kernel<kModeRaw>, kThreads, kSmemBytes);
     if (occ < 1) occ = 1;
     g_fbank_grid = occ * n_sm;  // every CTA resident at once: one wave, persistent
   }
@@ -1119,12 +1107,13 @@ int fbank_persistent_grid() {
 
 cudaError_t launch_fbank(const FbankLaunch& p, cudaStream_t s) {
   if (p.n_tiles <= 0) return cudaSuccess;
-  const int full = fbank_persistent_grid();
+  int full = fbank_persistent_grid();
+  if (p.grid_limit > 0 && p.grid_limit < full) full = p.grid_limit;  // tuning only (option "max_ctas")
   const int grid = p.n_tiles < full ? p.n_tiles : full;
-  if (p.fused)
-    fbank_tile_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(p);
+  if (p.epilogue == kEpiNormKnown)
+    fbank_tile_kernel<kModeNormKnown><<<grid, kThreads, kSmemBytes, s>>>(p);
   else
-    fbank_tile_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(p);
+    fbank_tile_kernel<kModeRaw><<<grid, kThreads, kSmemBytes, s>>>(p);
   return cudaGetLastError();
 }
 
@@ -1136,13 +1125,13 @@ cudaError_t launch_features(const FbankLaunch& p, cudaStream_t s) {
 
 cudaError_t launch_finalize(const FinalizeLaunch& p, cudaStream_t s) {
   if (p.n_utts <= 0) return cudaSuccess;
-  finalize_utt_kernel<<<p.n_utts, 128, 0, s>>>(p);
+  finalize_utt_kernel<<<p.n_utts, kFinalizeThreads, 0, s>>>(p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_apply(const ApplyLaunch& p, cudaStream_t s) {
   if (p.n_tiles <= 0) return cudaSuccess;
-  apply_kernel<<<p.n_tiles, kThreads, 0, s>>>(p);
+  apply_kernel<<<(p.n_tiles + kApplyTiles - 1) / kApplyTiles, kThreads, 0, s>>>(p);
   return cudaGetLastError();
 }
 

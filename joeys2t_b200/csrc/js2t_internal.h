@@ -72,18 +72,7 @@ struct FbankLaunch {
   const int* masks;     // [n_utts][n_masks][2] (start, width); first n_fmask are frequency masks
   int n_fmask, n_tmask;
   const float* mask_value;  // [n_utts]
-  // fused utterance CMVN (kEpiRaw + fused != 0): the CTA that completes an utterance's last tile
-  // reduces the per-tile statistics (fixed order), and normalises (+ masks) the whole utterance in
-  // place while its rows are L2-resident.  No CTA ever waits on another one.
-  int fused;
-  int norm_means, norm_vars;
-  int mask_value_mode;    // 0: mean of the CMVN output, 1: constant
-  float mask_value_const;
-  int* utt_counter;       // [n_utts], zero between launches
-  float* norm_mean;       // [n_utts][80]
-  float* norm_istd;       // [n_utts][80]
-  float* utt_mask_value;  // [n_utts]
-  double* stats_out;      // [n_utts][160] or nullptr
+  int grid_limit;  // tuning only: cap on the persistent grid (0 = all resident CTAs)
   int dbg_skip;  // tuning only: bit0 staging, bit1 FFT phase, bit2 mel, bit3 store, bit4 butterflies, bit5 exchange
   unsigned long long* dbg_times;  // [n_tiles][4] globaltimer stamps (debug / tuning only) or nullptr
 };

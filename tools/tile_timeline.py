@@ -13,14 +13,19 @@ from joeys2t_b200 import frontend, synthetic  # noqa: E402
 waves = synthetic.pooled_batch(256, seed=1234, lo=10.0, hi=15.0)
 packed = frontend.PackedPCM(waves)
 plan = frontend.Plan(packed.n_samples, packed.byte_off, packed.is_f32)
-plan.set_cmvn("utterance")
-if "--unfused" in sys.argv:
-    plan.set_option("force_unfused", 1)
+mode = sys.argv[sys.argv.index("--mode") + 1] if "--mode" in sys.argv else "utterance"
+if mode == "global":
+    plan.set_cmvn("global")
+    plan.set_global_stats(np.full(80, 5.0), np.full(80, 0.25))
+else:
+    plan.set_cmvn(mode)
+plan.set_option("fused_cmvn", 0 if "--unfused" in sys.argv else 1)
 plan.set_option("debug_times", 1)
 dev = packed.to_device()
 out = plan.empty_output()
-for _ in range(3):
-    plan.execute(dev, out)
+outs = [plan.empty_output() for _ in range(3)]
+for i in range(7):
+    plan.execute(dev, outs[i % 3])
 torch.cuda.synchronize()
 t = plan.debug_times().astype(np.int64)
 n = t.shape[0]
