@@ -596,8 +596,9 @@ int js2t_plan_set_option(js2t_plan* plan, const char* name, int value) {
   if (strcmp(name, "debug_times") == 0) {
     JS2T_CUDA(cudaSetDevice(plan->ctx->device));
     if (value != 0 && plan->d_dbg == nullptr) {
-      JS2T_CUDA(cudaMalloc(&plan->d_dbg, sizeof(unsigned long long) * 4 * plan->n_tiles));
-      JS2T_CUDA(cudaMemset(plan->d_dbg, 0, sizeof(unsigned long long) * 4 * plan->n_tiles));
+      // [n_tiles][4] per-tile stamps + [n_tiles][8 warps][8] per-warp stamps (JS2T_DBG builds)
+      JS2T_CUDA(cudaMalloc(&plan->d_dbg, sizeof(unsigned long long) * 68 * plan->n_tiles));
+      JS2T_CUDA(cudaMemset(plan->d_dbg, 0, sizeof(unsigned long long) * 68 * plan->n_tiles));
     } else if (value == 0 && plan->d_dbg != nullptr) {
       cudaFree(plan->d_dbg);
       plan->d_dbg = nullptr;
@@ -610,7 +611,7 @@ int js2t_plan_set_option(js2t_plan* plan, const char* name, int value) {
 int js2t_plan_debug_times(const js2t_plan* plan, unsigned long long* host_out, int64_t n_values) {
   if (plan == nullptr || host_out == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
   if (plan->d_dbg == nullptr) return fail(JS2T_ERR_STATE, "option debug_times is off");
-  if (n_values > 4ll * plan->n_tiles) n_values = 4ll * plan->n_tiles;
+  if (n_values > 68ll * plan->n_tiles) n_values = 68ll * plan->n_tiles;
   JS2T_CUDA(cudaSetDevice(plan->ctx->device));
   JS2T_CUDA(cudaMemcpy(host_out, plan->d_dbg, sizeof(unsigned long long) * n_values, cudaMemcpyDeviceToHost));
   return JS2T_OK;
