@@ -145,6 +145,13 @@ int js2t_ctx_set_tables(js2t_ctx* ctx, const float* window400, const float* mel8
                   "mel bank entry (filter %d, bin %d) = %g is outside the compiled-in two-band structure "
                   "(16 kHz, 512-point FFT, 80 bins, 20 Hz..Nyquist)", i / 256, i % 256, (double)mel80x256[i]);
   }
+  {
+    const int bad = check_mel_weights(wu, wd);
+    if (bad >= 0)
+      return fail(JS2T_ERR_TABLES,
+                  "mel bank weight of FFT bin %d differs from the compiled-in reference bank "
+                  "(torchaudio get_mel_banks(80, 512, 16000, 20, 0)); rebuild with gen_mel_structure.py", bad);
+  }
   // ---- window (x 0.5: folds the 1/2 of the real-FFT split; exact power-of-two scaling) --------
   std::vector<float> host(400 + 2 * 256 + 2 * 136);
   if (window400[0] != 0.f)

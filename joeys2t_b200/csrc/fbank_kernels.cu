@@ -25,13 +25,28 @@
 // FP32 throughout: the path is a small FP32 contraction, not a tensor-core workload.
 #include "js2t_internal.h"
 
+#include <string.h>
+
 #include "mel_structure.inc"
 
 namespace js2t {
 
-// mel weights in two-band form (tables.py: mel_two_band): wu[k] -> filter seg(k), wd[k] -> seg(k)-1
+// mel weights in two-band form (tables.py: mel_two_band): wu[k] -> filter seg(k), wd[k] -> seg(k)-1.
+// They are compile-time data (mel_structure.inc, generated from torchaudio's own get_mel_banks,
+// bit-exact): after unrolling every weight is an immediate operand of its FFMA — no constant-bank
+// loads in the mel stage.  js2t_ctx_set_tables rejects an uploaded bank that differs in any bit.
+#ifndef JS2T_MEL_IMM
+#define JS2T_MEL_IMM 1
+#endif
+#if JS2T_MEL_IMM
+__device__ constexpr float c_mel_wu[256] = {JS2T_MEL_WU_VALUES};
+__device__ constexpr float c_mel_wd[256] = {JS2T_MEL_WD_VALUES};
+#else
 __constant__ float c_mel_wu[256];
 __constant__ float c_mel_wd[256];
+#endif
+static const float h_mel_wu[256] = {JS2T_MEL_WU_VALUES};
+static const float h_mel_wd[256] = {JS2T_MEL_WD_VALUES};
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
@@ -47,7 +62,7 @@ constexpr float kLn2 = 0.693147180559945309417f;
 // The argument is >= eps, never denormal, so the .ftz form needs no range fix-up.
 __device__ __forceinline__ float log_floor(float x) {
   float l;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fmaxf(x, kLogFloor)));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));  // x <= floor (incl. 0 -> -inf) is replaced below
   return x > kLogFloor ? l * kLn2 : kLogOfFloor;
 }
 
@@ -727,23 +742,51 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
 #endif
         } else if (kMode != kModeNormKnown || JS2T_TEST_EPI == 1) {
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
+          if (nf == kTileFrames) {
+            // full tile (all but the last tile of an utterance): no row predicates, loads first
+            const float* src = sOut + 4 * warp * kOutStride + lane;
+            float* dst = out_tile + 4 * warp * kMel + lane;
+            float x[12];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int f = 4 * warp + i;
-            if (f < rows) {
-              const bool valid = f < nf;
-              const float* src = sOut + f * kOutStride + lane;
-              float* dst = out_tile + f * kMel + lane;
-              const float x0 = valid ? src[0] : p.pad_value;
-              const float x1 = valid ? src[32] : p.pad_value;
-              const float x2 = (valid && c2ok) ? src[64] : p.pad_value;
-              dst[0] = x0;
-              dst[32] = x1;
-              if (c2ok) dst[64] = x2;
-              if (valid) {
-                s0 += x0; q0 = fmaf(x0, x0, q0);
-                s1 += x1; q1 = fmaf(x1, x1, q1);
+            for (int i = 0; i < 4; ++i) {
+              x[3 * i] = src[i * kOutStride];
+              x[3 * i + 1] = src[i * kOutStride + 32];
+              x[3 * i + 2] = src[i * kOutStride + 64];  // lanes >= 16: row padding, zeroed below
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              dst[i * kMel] = x[3 * i];
+              dst[i * kMel + 32] = x[3 * i + 1];
+              if (c2ok) dst[i * kMel + 64] = x[3 * i + 2];
+            }
+            if (p.tile_stats != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float x2 = c2ok ? x[3 * i + 2] : 0.f;
+                s0 += x[3 * i]; q0 = fmaf(x[3 * i], x[3 * i], q0);
+                s1 += x[3 * i + 1]; q1 = fmaf(x[3 * i + 1], x[3 * i + 1], q1);
                 s2 += x2; q2 = fmaf(x2, x2, q2);
+              }
+            }
+          } else {
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) {
+              const int f = 4 * warp + i;
+              if (f < rows) {
+                const bool valid = f < nf;
+                const float* src = sOut + f * kOutStride + lane;
+                float* dst = out_tile + f * kMel + lane;
+                const float x0 = valid ? src[0] : p.pad_value;
+                const float x1 = valid ? src[32] : p.pad_value;
+                const float x2 = (valid && c2ok) ? src[64] : p.pad_value;
+                dst[0] = x0;
+                dst[32] = x1;
+                if (c2ok) dst[64] = x2;
+                if (valid) {
+                  s0 += x0; q0 = fmaf(x0, x0, q0);
+                  s1 += x1; q1 = fmaf(x1, x1, q1);
+                  s2 += x2; q2 = fmaf(x2, x2, q2);
+                }
               }
             }
           }
@@ -1112,10 +1155,28 @@ cudaError_t launch_fill_value(float* dst, int n, float value, cudaStream_t s) {
 }
 
 // ---- launchers -----------------------------------------------------------------------------------
+// Compares the two-band weights derived from the uploaded bank with the compiled-in ones (bit for
+// bit); returns the first differing bin or -1.  With -DJS2T_MEL_IMM=0 the weights are uploaded instead.
+int check_mel_weights(const float* wu256, const float* wd256) {
+  for (int k = 0; k < 256; ++k)
+    if (memcmp(&wu256[k], &h_mel_wu[k], 4) != 0 || memcmp(&wd256[k], &h_mel_wd[k], 4) != 0) {
+      if (wu256[k] == h_mel_wu[k] && wd256[k] == h_mel_wd[k]) continue;  // +0 / -0
+      return k;
+    }
+  return -1;
+}
+
 cudaError_t upload_mel_weights(const float* wu256, const float* wd256, cudaStream_t s) {
+#if JS2T_MEL_IMM
+  (void)wu256;
+  (void)wd256;
+  (void)s;
+  return cudaSuccess;
+#else
   cudaError_t e = cudaMemcpyToSymbolAsync(c_mel_wu, wu256, 256 * sizeof(float), 0, cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) return e;
   return cudaMemcpyToSymbolAsync(c_mel_wd, wd256, 256 * sizeof(float), 0, cudaMemcpyHostToDevice, s);
+#endif
 }
 
 static int g_fbank_grid = 0;

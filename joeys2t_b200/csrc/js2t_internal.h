@@ -114,6 +114,7 @@ struct ApplyLaunch {
 };
 
 cudaError_t upload_mel_weights(const float* wu256, const float* wd256, cudaStream_t s);
+int check_mel_weights(const float* wu256, const float* wd256);  // first bin that differs from the compiled-in weights, or -1
 cudaError_t launch_fbank(const FbankLaunch& p, cudaStream_t s);
 cudaError_t launch_features(const FbankLaunch& p, cudaStream_t s);  // p.pcm = feature rows
 cudaError_t launch_finalize(const FinalizeLaunch& p, cudaStream_t s);
