@@ -610,8 +610,16 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
               sa += __shfl_xor_sync(0xffffffffu, sa, off);
               sb += __shfl_xor_sync(0xffffffffu, sb, off);
             }
-            constexpr float kMeanScale = (float)((1.0 - (double)0.97f) / 400.0);
-            mc = pk(sa * kMeanScale, sb * kMeanScale);
+            // Exactness matters here: for a constant (DC-only) signal the sum is exactly 400 x, s / 400
+            // returns x, and x * (1 - 0.97f) [exactly representable] rounds to the very same float
+            // as the staged d = fma(-0.97f, x, x), so the frame becomes exact zeros and hits the log floor
+            // like the reference.  A fused scale factor (1 - 0.97f) / 400 would break that.
+            // s / 400 with one exact-residual correction step (3 FMA-class operations): when the
+            // quotient is representable, as for a constant signal, it is returned exactly.
+            const float ma0 = sa * 0.0025f, mb0 = sb * 0.0025f;
+            const float ma = fmaf(fmaf(-400.0f, ma0, sa), 0.0025f, ma0);
+            const float mb = fmaf(fmaf(-400.0f, mb0, sb), 0.0025f, mb0);
+            mc = pk(ma * kDcScale, mb * kDcScale);
           }
           const float* dA = sD + lA * kHop + 2 * r;
           const float* dB = sD + lB * kHop + 2 * r;

@@ -424,3 +424,153 @@ def test_utterance_cmvn_is_deterministic(fe, fixtures_pcm, with_masks):
         plan.close()
     assert torch.equal(outs[0][1], outs[1][1])  # identical fp64 statistics (fixed summation order)
     assert torch.equal(outs[0][0], outs[1][0])  # identical normalised features and fill values
+
+
+# ------------------------------------------------------------------------------------------------
+# more edge cases and properties (round 1d)
+# ------------------------------------------------------------------------------------------------
+def test_modified_mel_bank_is_rejected(fe):
+    """The mel weights are compile-time immediates; a context must refuse any other bank."""
+    import ctypes
+    from joeys2t_b200 import _lib, tables
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    _lib.check(lib.js2t_ctx_create(torch.cuda.current_device(), ctypes.byref(h)))
+    try:
+        win = np.ascontiguousarray(tables.povey_window(), np.float32)
+        mel = np.ascontiguousarray(tables.mel_banks(80), np.float32)
+        assert lib.js2t_ctx_set_tables(h, win.ctypes.data, mel.ctypes.data) == _lib.OK
+        bad = mel.copy()
+        k = int(np.flatnonzero(bad[40])[0])
+        bad[40, k] = np.nextafter(bad[40, k], np.float32(2.0))   # one ulp off
+        assert lib.js2t_ctx_set_tables(h, win.ctypes.data, bad.ctypes.data) == _lib.ERR_TABLES
+        assert b"mel bank" in lib.js2t_last_error()
+        bad = mel.copy()
+        bad[3, 200] = 0.5                                           # outside the two-band structure
+        assert lib.js2t_ctx_set_tables(h, win.ctypes.data, bad.ctypes.data) == _lib.ERR_TABLES
+        w2 = win.copy()
+        w2[0] = 1e-3                                                # window[0] must be exactly 0
+        assert lib.js2t_ctx_set_tables(h, w2.ctypes.data, mel.ctypes.data) == _lib.ERR_TABLES
+    finally:
+        lib.js2t_ctx_destroy(h)
+
+
+def test_extreme_amplitudes_and_dc(fe):
+    """Full-scale square wave, full-scale DC (mean removal must cancel it), a lone impulse and the
+    int16 extremes: log-mel within tolerance of the oracle, floored cells bit-identical."""
+    n = 16000
+    t = np.arange(n)
+    waves = [
+        np.where((t // 40) % 2 == 0, 32767, -32768).astype(np.int16),
+        np.full(n, 32767, np.int16),
+        np.full(n, -32768, np.int16),
+        np.zeros(n, np.int16),
+    ]
+    waves[3][7777] = 32767
+    out, nf = fe.fbank_cmvn_specaug_ragged(waves)
+    got = out.cpu().numpy()
+    off = 0
+    floor = np.float32(np.log(np.float32(1.1920928955078125e-07)))
+    for w, tt in zip(waves, nf):
+        ref = O.extract_fbank_features(w)
+        blk = got[off:off + tt]
+        off += tt
+        floored = ref == floor
+        assert (blk[floored] == floor).all(), "digital silence must hit the exact float32 floor"
+        assert np.abs(blk[~floored] - ref[~floored]).max(initial=0.0) <= LOGMEL_ATOL
+    # constant input: DC removal leaves exact zeros -> every cell is the floor
+    assert (got[nf[0]:nf[0] + nf[1]] == floor).all() and (got[nf[0] + nf[1]:nf[:3].sum()] == floor).all()
+
+
+def test_float64_and_tensor_inputs_match_int16(fe, fixtures_pcm):
+    """Q3/Q4: float64 / float32 tensors in [-1, 1) and int16 PCM give the same features."""
+    pcm, _ = fixtures_pcm
+    w = pcm[1]
+    a, _ = fe.fbank_cmvn_specaug_ragged([w])
+    b, _ = fe.fbank_cmvn_specaug_ragged([w.astype(np.float64) / 32768.0])
+    c, _ = fe.fbank_cmvn_specaug_ragged([torch.from_numpy(w.astype(np.float32) / np.float32(32768.0))[None]])
+    assert torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_tile_boundary_utterances_in_padded_layout(fe):
+    """Utterances of exactly 32/33/64/65 frames (tile boundaries), padded layout: rows past each
+    utterance hold the pad value, rows inside match the ragged layout bit for bit."""
+    rng = np.random.default_rng(3)
+    frames = [1, 31, 32, 33, 63, 64, 65, 96]
+    waves = [rng.integers(-9000, 9000, 400 + 160 * (f - 1)).astype(np.int16) for f in frames]
+    rag, nf = fe.fbank_cmvn_specaug_ragged(waves, cmvn={})
+    pad, nf2 = fe.fbank_cmvn_specaug_ragged(waves, cmvn={}, layout="padded", pad_value=-7.0)
+    assert nf.tolist() == frames == nf2.tolist() and pad.shape == (len(frames), 96, 80)
+    off = 0
+    for u, f in enumerate(frames):
+        assert torch.equal(pad[u, :f], rag[off:off + f])
+        assert (pad[u, f:] == -7.0).all()
+        off += f
+
+
+def test_host_pipeline_matches_direct_execution(fe):
+    """frontend.HostPipeline (three streams, pinned host buffers) returns what Plan.execute does."""
+    from joeys2t_b200 import synthetic
+    batches = [synthetic.pooled_batch(12, seed=50 + i, lo=1.0, hi=3.0) for i in range(5)]
+    packs = [fe.PackedPCM(b) for b in batches]
+    plans = [fe.Plan(p.n_samples, p.byte_off, p.is_f32).set_cmvn("utterance") for p in packs]
+    want = [pl.execute(pk.to_device()).cpu() for pl, pk in zip(plans, packs)]
+    pipe = fe.HostPipeline(n_slots=2, max_pcm_bytes=max(p.nbytes for p in packs),
+                           max_out_rows=max(p.out_rows for p in plans))
+    for i in range(len(packs)):
+        slot = pipe.submit(packs[i], plans[i])
+        got = pipe.result(slot).clone()
+        assert torch.equal(got, want[i]), i
+    # back-to-back submissions without reading in between (slots are recycled safely)
+    slots = [pipe.submit(packs[i], plans[i]) for i in range(2)]
+    for i, s in enumerate(slots):
+        assert torch.equal(pipe.result(s), want[i])
+    for pl in plans:
+        pl.close()
+
+
+def test_mustc_and_longform_full_size_properties(fe):
+    """Configs 3 and 4 at full size: frame counts, finiteness, CMVN moments, masks where drawn."""
+    import argparse
+    import bench
+    from joeys2t_b200.data_augmentation import SpecAugment, mask_tables_for_batch
+    for wl in ("cfg3", "cfg4"):
+        args = argparse.Namespace(workload=wl, utts=0, sweep_hours=0.0)
+        waves = bench.make_batch(args, 2345)
+        n_frames = [O.num_frames(len(w)) for w in waves]
+        table = nf_ = nt_ = None
+        if wl == "cfg3":
+            np.random.seed(2345)
+            table, nf_, nt_ = mask_tables_for_batch(SpecAugment(2, 27, 2, 100, 1.0), n_frames)
+        out, nf = fe.fbank_cmvn_specaug_ragged(waves, cmvn={}, masks=table, n_fmask=nf_ or 0, n_tmask=nt_ or 0)
+        assert nf.tolist() == n_frames and torch.isfinite(out).all()
+        off = 0
+        for u, t in enumerate(n_frames[:24]):
+            blk = out[off:off + t].double()
+            off += t
+            if table is None:
+                assert blk.mean(0).abs().max().item() < 2e-4
+                assert (blk.std(0, unbiased=False) - 1).abs().max().item() < 2e-3
+            else:  # masked cells hold one value per utterance, in exactly the drawn rectangles
+                m = np.zeros((t, 80), bool)
+                for f0, w in table[u, :nf_]:
+                    m[:, f0:f0 + w] = True
+                for t0, w in table[u, nf_:]:
+                    m[t0:t0 + w, :] = True
+                vals = blk.cpu().numpy()[m]
+                assert vals.size == 0 or np.ptp(vals) == 0.0
+        # spot-check against the oracle (unmasked utterance CMVN of the same waveform)
+        u = 5
+        start = int(np.sum(n_frames[:u]))
+        ref = O.cmvn_fp64(O.extract_fbank_features(waves[u]))
+        got = out[start:start + n_frames[u]].cpu().numpy()
+        if table is not None:
+            keep = np.ones_like(ref, bool)
+            for f0, w in table[u, :nf_]:
+                keep[:, f0:f0 + w] = False
+            for t0, w in table[u, nf_:]:
+                keep[t0:t0 + w, :] = False
+            err = np.abs(got - ref)[keep]
+            assert (err <= 5e-4 + 1e-4 * np.abs(ref[keep])).all()
+        else:
+            cmvn_close(got, ref)
