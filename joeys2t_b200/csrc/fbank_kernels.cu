@@ -67,8 +67,13 @@ __device__ __forceinline__ float log_floor(float x) {
 }
 
 // ---- shared memory carve-up (bytes) -------------------------------------------------------------
-constexpr int kDFloats = 5376;                    // >= kTileSamples (5360) + 16 zeroed tail floats
-constexpr int kPsumFloats = kDFloats / 8;         // 672 partial sums of 8 samples
+// The tile's PCM lands in one of two staging slots by bulk async copy (TMA 1-D) and is read from
+// there directly by the FFT warps: there is no separate staging pass and no float copy of the signal.
+//   int16 tile  : one slot  = 16 B lead-in + 5360 samples (+ 32 B that row 17 of the last frame pair
+//                 may touch; whatever is there is finite and meets a zero of the window)
+//   fp32 tile   : two slots = frames 0..15 | frames 16..31, each 16 B lead-in + 2816 samples
+constexpr int kSlotBytes = 11296;
+static_assert(kSlotBytes >= 16 + 2688 * 4 && kSlotBytes >= 16 + 2816 * 4 && kSlotBytes % 16 == 0, "slot size");
 constexpr int kExchStride = 17;                   // 8-byte words per row of the 16x16 transpose (padded)
 constexpr int kExchPerWarp = 2 * 16 * kExchStride;   // 8-byte words: two half-warps
 constexpr int kPStride = 34;                      // P[k][frame]: even (64-bit stores), 2k+f banks
@@ -76,21 +81,20 @@ constexpr int kPFloats = 257 * kPStride;
 constexpr int kOutStride = 81;                    // outTile[frame][mel], padded
 constexpr int kOutFloats = kTileFrames * kOutStride;
 
-constexpr int kOffD = 0;
-constexpr int kOffPsum = kOffD + kDFloats * 4;
-constexpr int kOffMean = kOffPsum + kPsumFloats * 4;
-constexpr int kOffWin = kOffMean + kTileFrames * 4;
+// Window and twiddle tables stay in shared memory.  (Tried in round 1 and removed: keeping every lane's
+// 82 private table words in tensor memory and reading them with tcgen05.ld.  Correct, but with two
+// co-resident CTAs streaming tcgen05.ld the SM delivered exactly the throughput of ONE CTA
+// (261 us vs 188 us per config-2 launch) — profiles/r1f_tmem_tables_ab.txt, tools/microbench_tmem.cu.)
+constexpr int kOffWin = 0;
 constexpr int kOffTw256 = kOffWin + (kFrameLen + 16) * 4;
 constexpr int kOffTw512 = kOffTw256 + 256 * 8;
 constexpr int kOffExch = kOffTw512 + 136 * 8;
 constexpr int kOffP = kOffExch + kWarps * kExchPerWarp * 8;
-constexpr int kOffRaw = (kOffP + kPFloats * 4 + 15) / 16 * 16;  // 16 B lead-in + int16 PCM of one tile (TMA target)
-constexpr int kRawBytes = 16 + kTileSamples * 2;
-constexpr int kOffBar = kOffRaw + ((kRawBytes + 15) / 16) * 16;
+constexpr int kOffRaw = (kOffP + kPFloats * 4 + 15) / 16 * 16;  // two PCM slots (TMA targets)
+constexpr int kOffBar = kOffRaw + 2 * kSlotBytes;
 constexpr int kSmemBytes = kOffBar + 16;
 static_assert(kOutFloats * 4 <= kWarps * kExchPerWarp * 8, "out tile aliases the exchange buffers");
-static_assert(kWarps * kStatsPerTile * 4 <= kDFloats * 4, "per-warp statistics alias the d buffer");
-static_assert(2 * kStatsPerTile * 8 + (2 * kMel + 4) * 4 <= kDFloats * 4, "fused-CMVN scratch aliases the d buffer");
+static_assert(kWarps * kStatsPerTile * 4 <= kPFloats * 4, "per-warp statistics alias the power spectrum");
 static_assert(kOffExch % 16 == 0 && kOffP % 16 == 0 && kOffTw256 % 16 == 0 && kOffWin % 16 == 0 &&
                   kOffRaw % 16 == 0 && kOffBar % 8 == 0,
               "alignment");
@@ -315,13 +319,33 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
       : "memory");
 }
 
-// bytes of int16 PCM staged for a tile: 16 bytes of lead-in (the 8 samples before the tile, when
-// the tile is not at the start of the utterance) + the tile's samples
+// PCM slots a tile occupies: none (pure padding), one (int16, or fp32 with <= 16 frames), two (fp32)
+__device__ __forceinline__ int tile_slots(const TileDesc& t) {
+  return t.nf == 0 ? 0 : (((t.flags & 1) && t.nf > 16) ? 2 : 1);
+}
+// One thread: start the bulk copies of a tile's PCM into slot(s) k, k+1 (mod 2).  Every slot starts
+// with 16 bytes of lead-in (the samples just before, when the tile is not at the start of the
+// utterance: pre-emphasis of the first sample needs its predecessor) followed by the samples.
 __device__ __forceinline__ void prefetch_tile(const FbankLaunch& p, const TileDesc& t, unsigned char* sRaw,
-                                              unsigned long long* bar) {
+                                              unsigned long long* bar, unsigned k) {
   const unsigned lead = t.frame0 > 0 ? 16u : 0u;
-  const unsigned bytes = (unsigned)(((t.nf - 1) * kHop + kFrameLen) * 2) + lead;
-  tma_load_1d(sRaw + 16 - lead, p.pcm + t.src_byte_off - lead, bytes, bar);
+  const unsigned s0 = k & 1u;
+  if (!(t.flags & 1)) {
+    const unsigned bytes = (unsigned)(((t.nf - 1) * kHop + kFrameLen) * 2) + lead;
+    tma_load_1d(sRaw + s0 * kSlotBytes + 16 - lead, p.pcm + t.src_byte_off - lead, bytes, bar + s0);
+  } else {
+    const int nf0 = t.nf < 16 ? t.nf : 16;  // frames of the first half
+    // the first half also holds the 16 samples past frame 15 that row 17 of frame pair (14, 15) reads
+    const int n0 = t.nf > 16 ? 2816 : (nf0 - 1) * kHop + kFrameLen;
+    tma_load_1d(sRaw + s0 * kSlotBytes + 16 - lead, p.pcm + t.src_byte_off - lead, (unsigned)(n0 * 4) + lead,
+                bar + s0);
+    if (t.nf > 16) {
+      const unsigned s1 = s0 ^ 1u;
+      const int n1 = (t.nf - 17) * kHop + kFrameLen;
+      tma_load_1d(sRaw + s1 * kSlotBytes, p.pcm + t.src_byte_off + 16 * kHop * 4 - 16, (unsigned)(n1 * 4) + 16u,
+                  bar + s1);
+    }
+  }
 }
 
 // ---- fused utterance CMVN helpers -------------------------------------------------------------------
@@ -383,14 +407,12 @@ constexpr int kMaxEpilogueMasks = 16;
 template <int kMode>
 __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaunch p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  float* sD = reinterpret_cast<float*>(smem + kOffD);
-  float* sPsum = reinterpret_cast<float*>(smem + kOffPsum);
   float* sWin = reinterpret_cast<float*>(smem + kOffWin);
   float2* sTw256 = reinterpret_cast<float2*>(smem + kOffTw256);
   float2* sTw512 = reinterpret_cast<float2*>(smem + kOffTw512);
   u64* sExch = reinterpret_cast<u64*>(smem + kOffExch);
   float* sOut = reinterpret_cast<float*>(smem + kOffExch);  // aliases sExch after the FFT phase
-  float* sStat = reinterpret_cast<float*>(smem + kOffD);    // aliases sD after the FFT phase
+  float* sStat = reinterpret_cast<float*>(smem + kOffP);    // aliases sP after the mel phase
   float* sP = reinterpret_cast<float*>(smem + kOffP);
   unsigned char* sRaw = smem + kOffRaw;
   unsigned long long* sBar = reinterpret_cast<unsigned long long*>(smem + kOffBar);
@@ -407,7 +429,10 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
   for (int i = tid; i < kFrameLen + 16; i += kThreads) sWin[i] = i < kFrameLen ? p.tab.window_half[i] : 0.f;
   sTw256[tid] = p.tab.tw256[tid];
   if (tid < 136) sTw512[tid] = p.tab.tw512[tid];
-  if (tid == 0) mbar_init(sBar, 1);
+  if (tid == 0) {
+    mbar_init(sBar, 1);
+    mbar_init(sBar + 1, 1);
+  }
   __shared__ float sGN[kMode == kModeNormKnown ? 2 * kMel : 1];                    // global mean | 1/std
   __shared__ int sMaskTab[kMode == kModeNormKnown ? 2 * kMaxEpilogueMasks : 1];  // this tile's utterance
   __shared__ float sMaskVal;
@@ -452,9 +477,11 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
   TileDesc cur = p.tiles[tile];
   TileDesc nxt = cur;
   if (next_tile < p.n_tiles) nxt = p.tiles[next_tile];
-  unsigned parity = 0;
+  // PCM slot ring: kslot = slots consumed so far; slot (k & 1) is in its (k >> 1)-th use, which is
+  // the phase its mbarrier completes next
+  unsigned kslot = 0;
 
-  if (is_sched && cur.nf > 0 && !(cur.flags & 1)) prefetch_tile(p, cur, sRaw, sBar);
+  if (is_sched && cur.nf > 0) prefetch_tile(p, cur, sRaw, sBar, 0);
 
   while (true) {
     JS2T_WSTAMP(0)
@@ -475,7 +502,12 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
     if (is_sched) sClaim = atomicAdd(p.sched, 1);  // claim two ahead; consumed at the end of the iteration
 #endif
     const bool has_next = next_tile < p.n_tiles;
-    const bool next_tma = has_next && nxt.nf > 0 && !(nxt.flags & 1);
+    // The next tile's PCM is fetched a whole iteration ahead when a slot is free for it (always, for
+    // int16 tiles), otherwise as soon as this tile's samples have been consumed.
+    const unsigned cur_slots = (unsigned)tile_slots(cur);
+    const bool next_tma = has_next && nxt.nf > 0;
+    const bool next_early = next_tma && cur_slots + (unsigned)tile_slots(nxt) <= 2u;
+    if (is_sched && next_early) prefetch_tile(p, nxt, sRaw, sBar, kslot + cur_slots);
     if (kMode == kModeNormKnown && p.masks != nullptr) {
       // this utterance's mask table and fill value -> shared memory (read two barriers later)
       // (cp.async: fire and forget now, waited for just before the barrier in front of the epilogue,
@@ -500,88 +532,12 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
       if (p.tile_stats != nullptr && tid < kStatsPerTile)
         p.tile_stats[(long long)tile * kStatsPerTile + tid] = 0.f;
       for (int e = tid; e < rows * kMel; e += kThreads) out_tile[e] = p.pad_value;
-      if (is_sched && next_tma) prefetch_tile(p, nxt, sRaw, sBar);
     } else {
-      // ---- phase 1: stage PCM as d[j] = x[j] - 0.97 x[j-1] and 8-sample partial sums ----------------
-      const int n_chunks = 20 * nf + 30;  // ((nf - 1) * 160 + 400) / 8
-      if (tid < 16) sD[8 * n_chunks + tid] = 0.f;  // the 16 floats past the tile that frame loads may touch
-      if (!(cur.flags & 1)) {
-        // int16 PCM, already in shared memory (bulk async copy issued one tile ago)
-        mbar_wait(sBar, parity);
-        parity ^= 1u;
-        if (!JS2T_SKIP(1)) {
-        const int4* raw4 = reinterpret_cast<const int4*>(sRaw + 16);
-        const unsigned* rawu = reinterpret_cast<const unsigned*>(sRaw + 16);
-#pragma unroll 1
-        for (int c = tid; c < n_chunks; c += kThreads) {
-          const int4 a = raw4[c];
-          // int16 -> float without the (slow, 16 lanes/clk) I2F unit: 0x4B000000 | (s ^ 0x8000) is the
-          // float 8388608 + (s + 32768); subtracting 8421376 is exact.
-          // Previous sample = high half of the previous 32-bit word: from the neighbouring lane, or
-          // (lane 0) from shared memory — at the very first sample of the utterance that word is the
-          // unloaded lead-in; any bit pattern converts to a finite value, and it only reaches frame
-          // position 0 where the povey window is exactly 0.
-          unsigned wp = __shfl_up_sync(__activemask(), (unsigned)a.w, 1);
-          if (lane == 0) wp = rawu[4 * c - 1];
-          constexpr float kMagic = 8421376.0f;
-          const unsigned w0 = (unsigned)a.x ^ 0x80008000u, w1 = (unsigned)a.y ^ 0x80008000u,
-                         w2 = (unsigned)a.z ^ 0x80008000u, w3 = (unsigned)a.w ^ 0x80008000u;
-          float x[8];
-          x[0] = __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7410)) - kMagic;
-          x[1] = __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7432)) - kMagic;
-          x[2] = __uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7410)) - kMagic;
-          x[3] = __uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7432)) - kMagic;
-          x[4] = __uint_as_float(__byte_perm(w2, 0x4B000000u, 0x7410)) - kMagic;
-          x[5] = __uint_as_float(__byte_perm(w2, 0x4B000000u, 0x7432)) - kMagic;
-          x[6] = __uint_as_float(__byte_perm(w3, 0x4B000000u, 0x7410)) - kMagic;
-          x[7] = __uint_as_float(__byte_perm(w3, 0x4B000000u, 0x7432)) - kMagic;
-          const float xm1 = __uint_as_float(__byte_perm(wp ^ 0x80008000u, 0x4B000000u, 0x7432)) - kMagic;
-          float4 d0, d1;
-          d0.x = fmaf(-kPreemph, xm1, x[0]);
-          d0.y = fmaf(-kPreemph, x[0], x[1]);
-          d0.z = fmaf(-kPreemph, x[1], x[2]);
-          d0.w = fmaf(-kPreemph, x[2], x[3]);
-          d1.x = fmaf(-kPreemph, x[3], x[4]);
-          d1.y = fmaf(-kPreemph, x[4], x[5]);
-          d1.z = fmaf(-kPreemph, x[5], x[6]);
-          d1.w = fmaf(-kPreemph, x[6], x[7]);
-          reinterpret_cast<float4*>(sD)[2 * c] = d0;
-          reinterpret_cast<float4*>(sD)[2 * c + 1] = d1;
-          sPsum[c] = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
-        }
-        }
-      } else {
-        // float32 PCM in [-1, 1): straight from global memory (no staging buffer of that size)
-        const float* src = reinterpret_cast<const float*>(p.pcm + cur.src_byte_off);
-        const bool at_start = cur.frame0 == 0;
-#pragma unroll 1
-        for (int c = tid; c < n_chunks; c += kThreads) {
-          const int4 a = ldg_stream_int4(src + 8 * c);
-          const int4 b = ldg_stream_int4(src + 8 * c + 4);
-          float x[8];
-          x[0] = __int_as_float(a.x) * 32768.f; x[1] = __int_as_float(a.y) * 32768.f;
-          x[2] = __int_as_float(a.z) * 32768.f; x[3] = __int_as_float(a.w) * 32768.f;
-          x[4] = __int_as_float(b.x) * 32768.f; x[5] = __int_as_float(b.y) * 32768.f;
-          x[6] = __int_as_float(b.z) * 32768.f; x[7] = __int_as_float(b.w) * 32768.f;
-          const float xm1 = (c == 0 && at_start) ? x[0] : __ldg(src + 8 * c - 1) * 32768.f;
-          float4 d0, d1;
-          d0.x = fmaf(-kPreemph, xm1, x[0]);
-          d0.y = fmaf(-kPreemph, x[0], x[1]);
-          d0.z = fmaf(-kPreemph, x[1], x[2]);
-          d0.w = fmaf(-kPreemph, x[2], x[3]);
-          d1.x = fmaf(-kPreemph, x[3], x[4]);
-          d1.y = fmaf(-kPreemph, x[4], x[5]);
-          d1.z = fmaf(-kPreemph, x[5], x[6]);
-          d1.w = fmaf(-kPreemph, x[6], x[7]);
-          reinterpret_cast<float4*>(sD)[2 * c] = d0;
-          reinterpret_cast<float4*>(sD)[2 * c + 1] = d1;
-          sPsum[c] = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
-        }
-      }
+      // ---- phase 1: wait for this tile's PCM (bulk async copy issued one tile ago) ---------------------
+      const bool f32 = (cur.flags & 1) != 0;
+      mbar_wait(sBar + (kslot & 1u), (kslot >> 1) & 1u);
+      if (cur_slots == 2u) mbar_wait(sBar + ((kslot + 1u) & 1u), ((kslot + 1u) >> 1) & 1u);
       JS2T_WSTAMP(1)
-      __syncthreads();
-      // the staging buffer is free again: start fetching the next tile's PCM behind the compute below
-      if (is_sched && next_tma) prefetch_tile(p, nxt, sRaw, sBar);
 
       // ---- phase 2: two frames per half-warp (packed), four per warp -> power spectrum P[k][frame] ----
       if (4 * warp < nf && !JS2T_SKIP(2)) {
@@ -590,21 +546,72 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
         u64* exch = sExch + warp * kExchPerWarp + half * (16 * kExchStride);
         const int partner = (lane & 16) | ((16 - r) & 15);
         const int fA = 4 * warp + 2 * half;  // frames fA, fA + 1 (even: 64-bit P stores)
-        const int lA = min(fA, nf - 1), lB = min(fA + 1, nf - 1);  // past-the-end frames redo the last one
+        // past-the-end frame pairs redo the last valid pair (results land in unused columns of P)
+        const int lA = min(fA, (nf - 1) & ~1);
         C2 v[16];
         {
-          // per-frame DC mean (kaldi.py:183-186) of the two frames from the 8-sample partial sums
-          // (frame l covers partial sums [20 l, 20 l + 50)), reduced over the half-warp and
-          // pre-multiplied by (1 - 0.97): (x_j - m) - 0.97 (x_{j-1} - m) = d_j - 0.03 m
+          // The lane's share of the two frames, straight from the PCM slot.  The hop is 160 = 5 x 32
+          // samples, so with rows of 32 samples counted from the start of frame lA, frame lA covers
+          // rows 0..12 and frame lA + 1 rows 5..17 with the SAME lane <-> sample mapping: lane r owns
+          // samples 2r, 2r + 1 of every row (= complex point n = r + 16 row of z[n] = y[2n] + i y[2n+1]),
+          // and 18 loads serve both frames.  Per sample: x (int16, or float * 2^15: exact, Q4),
+          // d = x[j] - 0.97 x[j-1], and the running sums of x for the two DC means.
+          //   (x_j - m) - 0.97 (x_{j-1} - m) = d_j - 0.03 m, and window[0] = 0 exactly kills the
+          //   replicate-padded first sample (kaldi.py:193-198), so d does not depend on the frame.
+          float de[18], dO[18];  // d of the even / odd sample of the pair
+          float sa = 0.f, sb = 0.f, mid = 0.f;
+          const unsigned char* slot0 = sRaw + (kslot & 1u) * kSlotBytes;
+          if (!f32) {
+            const unsigned* rw = reinterpret_cast<const unsigned*>(slot0 + 16) + 80 * lA + r;
+            constexpr float kMagic = 8421376.0f;
+#pragma unroll
+            for (int n = 0; n < 18; ++n) {
+              // int16 -> float without the (slow, 16 lanes/clk) I2F unit: 0x4B000000 | (s ^ 0x8000) is the
+              // float 8388608 + (s + 32768); subtracting 8421376 is exact.  The predecessor of sample 2r
+              // is the high half of the previous word (at the very first sample of the utterance that
+              // is the unloaded lead-in: any bit pattern converts to a finite value, and it only reaches
+              // frame position 0 where the povey window is exactly 0).
+              const unsigned wc = rw[16 * n] ^ 0x80008000u;
+              const unsigned wp = rw[16 * n - 1] ^ 0x80008000u;
+              const float x0 = __uint_as_float(__byte_perm(wc, 0x4B000000u, 0x7410)) - kMagic;
+              const float x1 = __uint_as_float(__byte_perm(wc, 0x4B000000u, 0x7432)) - kMagic;
+              const float xm = __uint_as_float(__byte_perm(wp, 0x4B000000u, 0x7432)) - kMagic;
+              de[n] = fmaf(-kPreemph, xm, x0);
+              dO[n] = fmaf(-kPreemph, x0, x1);
+              const float sx = x0 + x1;
+              if (n < 5) sa += sx;
+              else if (n < 12) mid += sx;
+              else if (n == 12) { sb += sx; if (r < 8) sa += sx; }
+              else if (n < 17) sb += sx;
+              else if (r < 8) sb += sx;
+            }
+          } else {
+            // float32 PCM in [-1, 1): frames 16..31 of the tile live in the other slot
+            const unsigned char* sl = (fA >= 16) ? sRaw + ((kslot + 1u) & 1u) * kSlotBytes : slot0;
+            const float* rf = reinterpret_cast<const float*>(sl + 16) + kHop * (lA & 15) + 2 * r;
+            const bool first = cur.frame0 == 0 && lA == 0 && r == 0;  // sample 0 of the utterance
+#pragma unroll
+            for (int n = 0; n < 18; ++n) {
+              const float2 c = *reinterpret_cast<const float2*>(rf + 32 * n);
+              const float x0 = c.x * 32768.f, x1 = c.y * 32768.f;
+              float xm = rf[32 * n - 1] * 32768.f;
+              if (n == 0 && first) xm = x0;  // the lead-in was not loaded (it could hold a NaN pattern)
+              de[n] = fmaf(-kPreemph, xm, x0);
+              dO[n] = fmaf(-kPreemph, x0, x1);
+              const float sx = x0 + x1;
+              if (n < 5) sa += sx;
+              else if (n < 12) mid += sx;
+              else if (n == 12) { sb += sx; if (r < 8) sa += sx; }
+              else if (n < 17) sb += sx;
+              else if (r < 8) sb += sx;
+            }
+          }
+          sa += mid;
+          sb += mid;
+          // per-frame DC mean (kaldi.py:183-186), reduced over the half-warp and pre-multiplied by
+          // (1 - 0.97)
           u64 mc;
           {
-            const float* pa = sPsum + 20 * lA + r;
-            const float* pb = sPsum + 20 * lB + r;
-            float sa = (pa[0] + pa[16]) + pa[32], sb = (pb[0] + pb[16]) + pb[32];
-            if (r < 2) {
-              sa += pa[48];
-              sb += pb[48];
-            }
 #pragma unroll
             for (int off = 8; off >= 1; off >>= 1) {
               sa += __shfl_xor_sync(0xffffffffu, sa, off);
@@ -612,7 +619,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
             }
             // Exactness matters here: for a constant (DC-only) signal the sum is exactly 400 x, s / 400
             // returns x, and x * (1 - 0.97f) [exactly representable] rounds to the very same float
-            // as the staged d = fma(-0.97f, x, x), so the frame becomes exact zeros and hits the log floor
+            // as d = fma(-0.97f, x, x), so the frame becomes exact zeros and hits the log floor
             // like the reference.  A fused scale factor (1 - 0.97f) / 400 would break that.
             // s / 400 with one exact-residual correction step (3 FMA-class operations): when the
             // quotient is representable, as for a constant signal, it is returned exactly.
@@ -621,17 +628,16 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
             const float mb = fmaf(fmaf(-400.0f, mb0, sb), 0.0025f, mb0);
             mc = pk(ma * kDcScale, mb * kDcScale);
           }
-          const float* dA = sD + lA * kHop + 2 * r;
-          const float* dB = sD + lB * kHop + 2 * r;
           const float* wfr = sWin + 2 * r;
 #pragma unroll
-          for (int n1 = 0; n1 < 13; ++n1) {  // n1 == 12: lanes r >= 8 read the zeroed window tail
-            const float2 a = *reinterpret_cast<const float2*>(dA + 32 * n1);
-            const float2 b = *reinterpret_cast<const float2*>(dB + 32 * n1);
+          for (int n1 = 0; n1 < 13; ++n1) {
             const float2 w = *reinterpret_cast<const float2*>(wfr + 32 * n1);
-            v[n1].re = mul2(sub2(pk(a.x, b.x), mc), bc(w.x));
-            v[n1].im = mul2(sub2(pk(a.y, b.y), mc), bc(w.y));
+            v[n1].re = mul2(sub2(pk(de[n1], de[n1 + 5]), mc), bc(w.x));
+            v[n1].im = mul2(sub2(pk(dO[n1], dO[n1 + 5]), mc), bc(w.y));
           }
+          // row 12: lanes r >= 8 are past sample 399 of the frame (window = 0); what they read may lie
+          // beyond the staged samples and, for float PCM, need not be finite
+          if (r >= 8) v[12] = C2{0ull, 0ull};
           v[13] = v[14] = v[15] = C2{0ull, 0ull};
         }
         // pass 1: DFT over n1 (lane = n2 = r), then twiddle by W_256^(n2*k1)
@@ -665,7 +671,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
         float* Pf = sP + fA;
         const bool r0 = (r == 0);
 #pragma unroll
-        for (int j = 0; j < 9; ++j) {
+        for (int j = 0; j < 8; ++j) {
           // partner register index: 15 - j, except in lane r == 0 where it is (16 - j) & 15
           const C2 ma = v[(15 - j) & 15];
           const C2 mb = v[(16 - j) & 15];
@@ -676,7 +682,6 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
           const float q1 = __shfl_sync(0xffffffffu, r0 ? t1 : s1, partner);
           const float q2 = __shfl_sync(0xffffffffu, r0 ? t2 : s2, partner);
           const float q3 = __shfl_sync(0xffffffffu, r0 ? t3 : s3, partner);
-          if (j == 8 && !r0) continue;  // k = 128 exists only in lane r == 0
           const C2 z = v[j];
           const C2 zp = C2{pk(q0, q1), pk(q2, q3)};
           const int k = r + 16 * j;
@@ -690,9 +695,21 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
           *reinterpret_cast<u64*>(Pf + k * kPStride) = fma2(ar, ar, mul2(ai, ai));
           *reinterpret_cast<u64*>(Pf + (256 - k) * kPStride) = fma2(br, br, mul2(bi, bi));
         }
+        if (r0) {  // k = 128 is its own partner bin (no shuffle); same arithmetic as above
+          const C2 z = v[8];
+          const float2 w = sTw512[128];
+          const u64 er = add2(z.re, z.re), ei = sub2(z.im, z.im);
+          const u64 orr = add2(z.im, z.im), oi = sub2(z.re, z.re);
+          const u64 tr = fma2(oi, bc(-w.y), mul2(orr, bc(w.x)));
+          const u64 ti = fma2(orr, bc(w.y), mul2(oi, bc(w.x)));
+          const u64 ar = add2(er, tr), ai = add2(ei, ti);
+          *reinterpret_cast<u64*>(Pf + 128 * kPStride) = fma2(ar, ar, mul2(ai, ai));
+        }
       }
       JS2T_WSTAMP(3)
       __syncthreads();
+      // this tile's PCM slots are free again
+      if (is_sched && next_tma && !next_early) prefetch_tile(p, nxt, sRaw, sBar, kslot + cur_slots);
 
       // ---- phase 3: mel filterbank + log, lane = frame, warp = run of filters -------------------------
       {
@@ -854,6 +871,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
     JS2T_WSTAMP(5)
     __syncthreads();  // sD / sOut / sStat are rewritten by the next tile; sClaim / sDesc are visible
     tile = next_tile;
+    kslot += cur_slots;
     cur = nxt;
     next_tile = sClaim;
     if (next_tile < p.n_tiles) nxt = sDesc;
@@ -861,6 +879,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
 #else
     __syncthreads();  // sD / sOut / sStat are rewritten by the next tile; sClaim is visible
     tile = next_tile;
+    kslot += cur_slots;
     cur = nxt;
     next_tile = sClaim;
     if (next_tile < p.n_tiles) nxt = p.tiles[next_tile];

@@ -25,11 +25,11 @@ n = int(np.sum((plan.n_frames + 31) // 32))
 buf = np.zeros(68 * n, np.uint64)
 _lib.check(_lib.load().js2t_plan_debug_times(plan._h, buf.ctypes.data, buf.size))
 w = buf[4 * n:].reshape(n, 8, 8).astype(np.int64)  # [tile][warp][slot]
-w[:, :, 2] = w[:, :, 1]  # the DC-mean barrier is gone: slot 2 is no longer stamped
+w[:, :, 2] = w[:, :, 1]  # slot 1 = PCM of the tile has arrived (mbarrier); slot 2 is not stamped
 ok = (w[:, :, :6] > 0).all(axis=(1, 2))
 w = w[ok]
 print(f"{ok.sum()} of {n} tiles with complete stamps")
-names = ["top->staged", "(unused)", "staged->fft done", "fft->mel done", "mel->store done"]
+names = ["top->PCM ready", "(unused)", "PCM->fft done", "fft->mel done", "mel->store done"]
 # arrival of each warp at barrier s relative to the release of barrier s-1 (= max arrival over warps at s-1)
 for s in (1, 3, 4, 5):
     rel = w[:, :, s] - w[:, :, s - 1].max(axis=1, keepdims=True)
