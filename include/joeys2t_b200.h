@@ -162,6 +162,20 @@ int js2t_global_stats_allreduce(void* nccl_comm, double* accum_dev, void* stream
 int js2t_global_stats_finalize(js2t_plan* plan, const double* accum_dev, void* stream);
 int js2t_normalize_execute(js2t_plan* plan, float* out_dev, void* stream);
 
+/* ---- PCM ingest: 48 kHz -> 16 kHz -------------------------------------------
+ * Replaces scripts/gradio_demo.py:35-45 reformat_freq for sr == 48000:
+ *     y = ((y / max(np.max(y), 1)) * 32767).reshape((-1, 3)).mean(axis=1).astype("int16")
+ * i.e. peak-normalise by the (signed) maximum, average blocks of three samples, truncate to int16.
+ * Same arithmetic, same order and precision as numpy evaluates it: float64 for int16 input,
+ * float32 for float32 input — results are bit-identical to the reference expression.
+ *   src_dev       n_samples samples (int16 when is_f32 == 0, float32 otherwise); n_samples % 3 == 0
+ *                 (the reference's reshape raises otherwise -> JS2T_ERR_INVALID)
+ *   dst_dev       n_samples / 3 int16 samples
+ *   workspace_dev 8 bytes of device scratch (the maximum), owned by the caller
+ * Asynchronous on `stream`. */
+int js2t_reformat_48k_to_16k(js2t_ctx* ctx, const void* src_dev, int is_f32, int64_t n_samples,
+                             int16_t* dst_dev, void* workspace_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,7 @@ from pathlib import Path
 CSRC = Path(__file__).resolve().parent / "csrc"
 # JS2T_LIB selects another build of the same library (tuning A/B runs: tools/build_variant.py)
 LIB_PATH = Path(os.environ["JS2T_LIB"]).resolve() if os.environ.get("JS2T_LIB") else CSRC / "libjoeys2t_b200.so"
-SOURCES = ["fbank_kernels.cu", "capi.cu"]
+SOURCES = ["fbank_kernels.cu", "ingest_kernels.cu", "capi.cu"]
 HEADERS = ["js2t_internal.h", "mel_structure.inc", "../../include/joeys2t_b200.h"]
 
 # status codes (include/joeys2t_b200.h)
@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = [
     "js2t_features_execute", "js2t_plan_enable_profiling", "js2t_plan_kernel_times_ms",
     "js2t_plan_set_option", "js2t_plan_debug_times", "js2t_plan_utt_stats", "js2t_plan_copy_utt_stats", "js2t_global_stats_accumulate",
     "js2t_global_stats_allreduce", "js2t_global_stats_finalize", "js2t_normalize_execute",
+    "js2t_reformat_48k_to_16k",
 ]
 
 
@@ -115,6 +116,7 @@ def _declare(lib):
     lib.js2t_global_stats_allreduce.argtypes = [vp, vp, vp]
     lib.js2t_global_stats_finalize.argtypes = [vp, vp, vp]
     lib.js2t_normalize_execute.argtypes = [vp, vp, vp]
+    lib.js2t_reformat_48k_to_16k.argtypes = [vp, vp, i32, i64, vp, vp, vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is c.c_int and name not in ("js2t_version",):

@@ -697,4 +697,19 @@ int js2t_normalize_execute(js2t_plan* plan, float* out_dev, void* stream_) {
   return JS2T_OK;
 }
 
+int js2t_reformat_48k_to_16k(js2t_ctx* ctx, const void* src_dev, int is_f32, int64_t n_samples,
+                             int16_t* dst_dev, void* workspace_dev, void* stream_) {
+  if (ctx == nullptr || workspace_dev == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
+  if (n_samples < 0 || n_samples % 3 != 0)
+    return fail(JS2T_ERR_INVALID, "cannot reshape array of size %lld into shape (-1, 3)", (long long)n_samples);
+  if (n_samples == 0) return JS2T_OK;
+  if (src_dev == nullptr || dst_dev == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
+  if ((reinterpret_cast<uintptr_t>(src_dev) & 15) != 0 || (reinterpret_cast<uintptr_t>(dst_dev) & 15) != 0)
+    return fail(JS2T_ERR_INVALID, "src_dev and dst_dev must be 16-byte aligned");
+  JS2T_CUDA(cudaSetDevice(ctx->device));
+  JS2T_CUDA(launch_reformat_48k_to_16k(src_dev, is_f32, (long long)n_samples, dst_dev,
+                                       static_cast<int*>(workspace_dev), (cudaStream_t)stream_));
+  return JS2T_OK;
+}
+
 }  // extern "C"

@@ -126,6 +126,9 @@ cudaError_t launch_global_accumulate(const double* utt_stats, const UttDesc* utt
 cudaError_t launch_global_finalize(const double* accum, int norm_means, int norm_vars,
                                    float* mean, float* istd, cudaStream_t s);
 cudaError_t launch_fill_value(float* dst, int n, float value, cudaStream_t s);
+// 48 kHz -> 16 kHz ingest (scripts/gradio_demo.py:35-45); ws = one int of device scratch
+cudaError_t launch_reformat_48k_to_16k(const void* src, int is_f32, long long n_samples, short* dst, int* ws,
+                                       cudaStream_t s);
 int fbank_smem_bytes();
 int fbank_persistent_grid();  // CTAs of the persistent fbank kernel on the current device
 

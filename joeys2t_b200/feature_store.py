@@ -1,0 +1,183 @@
+# coding: utf-8
+"""
+On-disk feature store — SURVEY.md §8(f-3): the reference's ``npy``-in-``ZIP_STORED`` archive with a
+``<zip name>:<byte offset>:<byte size>`` manifest and the TSV columns ``id, src, n_frames, trg``
+(``scripts/audiodata_utils.py:45-98``; reader: ``joeynmt/helpers_for_audio.py:72-89,100-127``;
+producer: ``scripts/prepare_librispeech.py:60-112``, ``prepare_mustc.py``, ``prepare_europarl.py``,
+``prepare_openslr.py``).
+
+``create_zip`` / ``get_zip_manifest`` / ``save_tsv`` / ``load_tsv`` keep the reference's names,
+arguments and results.  :class:`ZipFeatureWriter` and :func:`extract_corpus` are the batched
+replacement of the prep scripts' per-utterance loop (``_extract`` → ``np.save`` → ``create_zip`` →
+``get_zip_manifest``): whole batches of utterances go through the fused GPU front-end and their
+``.npy`` images are written straight into the archive, with the manifest entry of every member
+known at write time.  A member's payload is byte-identical to what ``np.save`` writes, its offset is
+what ``get_zip_manifest`` computes (``header_offset + 30 + len(filename)``, :52), so archives are
+interchangeable with the reference's in both directions.
+"""
+import csv
+import io
+import zipfile
+from pathlib import Path
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from joeys2t_b200.helpers_for_audio import _is_npy_data
+
+
+def get_zip_manifest(zip_path: Path, npy_root: Optional[Path] = None) -> Dict[str, str]:
+    """``audiodata_utils.py:45-63`` — ``{utt_id: "<zip name>:<offset>:<size>"}`` for every member."""
+    manifest = {}
+    with zipfile.ZipFile(zip_path, mode="r") as f:
+        info = f.infolist()
+    # retrieve offsets
+    with zip_path.open("rb") as f:
+        for i in info:
+            utt_id = Path(i.filename).stem
+            offset, file_size = i.header_offset + 30 + len(i.filename), i.file_size
+            f.seek(offset)
+            data = f.read(file_size)
+            assert len(data) > 1 and _is_npy_data(data), (utt_id, len(data))
+            manifest[utt_id] = f"{zip_path.name}:{offset}:{file_size}"
+            # sanity check
+            if npy_root is not None:
+                byte_data = np.load(io.BytesIO(data))
+                npy_data = np.load((npy_root / f"{utt_id}.npy").as_posix())
+                assert np.allclose(byte_data, npy_data)
+    return manifest
+
+
+def create_zip(data_root: Path, zip_path: Path) -> None:
+    """``audiodata_utils.py:66-73`` — pack every ``*.npy`` of ``data_root`` uncompressed."""
+    paths = list(data_root.glob("*.npy"))
+    with zipfile.ZipFile(zip_path, "w", zipfile.ZIP_STORED) as f:
+        for path in paths:
+            try:
+                f.write(path, arcname=path.name)
+            except Exception as e:  # pylint: disable=broad-except
+                raise RuntimeError(f"{path}") from e
+
+
+def save_tsv(df, path: Path, header: bool = True) -> None:
+    """``audiodata_utils.py:76-85``"""
+    df.to_csv(path.as_posix(), sep="\t", header=header, index=False, encoding="utf-8",
+              escapechar="\\", quoting=csv.QUOTE_NONE)
+
+
+def load_tsv(path: Path):
+    """``audiodata_utils.py:88-98``"""
+    import pandas as pd  # pylint: disable=import-outside-toplevel
+    return pd.read_csv(path.as_posix(), sep="\t", header=0, encoding="utf-8", escapechar="\\",
+                       quoting=csv.QUOTE_NONE, na_filter=False)
+
+
+def npy_bytes(features: np.ndarray) -> bytes:
+    """The exact byte image ``np.save`` writes for ``features`` (magic ``\\x93NUMPY``)."""
+    buf = io.BytesIO()
+    np.save(buf, np.ascontiguousarray(features))
+    return buf.getvalue()
+
+
+class ZipFeatureWriter:
+    """Append ``(utt_id, features)`` pairs to a ``ZIP_STORED`` archive and collect the manifest.
+
+    Equivalent to ``np.save(feature_root / f"{id}.npy")`` for every utterance followed by
+    ``create_zip`` and ``get_zip_manifest`` — without the intermediate files and without
+    re-reading the archive.
+    """
+
+    def __init__(self, zip_path: Path, mode: str = "w"):
+        self.zip_path = Path(zip_path)
+        self._zf = zipfile.ZipFile(self.zip_path, mode, zipfile.ZIP_STORED, allowZip64=True)
+        self.manifest: Dict[str, str] = {}
+        self.n_frames: Dict[str, int] = {}
+
+    def add(self, utt_id: str, features: np.ndarray) -> str:
+        assert features.ndim == 2, "spectrogram must be a 2-D array."
+        if utt_id in self.manifest:
+            raise ValueError(f"duplicate utterance id {utt_id!r}")
+        name = f"{utt_id}.npy"
+        data = npy_bytes(features)
+        info = zipfile.ZipInfo(name)  # fixed timestamp: archives are reproducible
+        info.compress_type = zipfile.ZIP_STORED
+        self._zf.writestr(info, data)
+        written = self._zf.getinfo(name)
+        # local file header = 30 bytes + name (+ extra, empty here) — audiodata_utils.py:52
+        offset = written.header_offset + 30 + len(name.encode("utf-8")) + len(written.extra)
+        entry = f"{self.zip_path.name}:{offset}:{len(data)}"
+        self.manifest[utt_id] = entry
+        self.n_frames[utt_id] = int(features.shape[0])
+        return entry
+
+    def close(self) -> Dict[str, str]:
+        self._zf.close()
+        return self.manifest
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+
+def extract_corpus(
+    items: Iterable[Tuple[str, "np.ndarray"]],
+    zip_path: Path,
+    batch_utterances: int = 256,
+    batch_seconds: float = 4000.0,
+    sample_rate: int = 16000,
+) -> Tuple[Dict[str, str], Dict[str, int], List[Tuple[str, str]]]:
+    """GPU replacement of the prep scripts' extraction loop (``prepare_librispeech.py:74-107``).
+
+    ``items`` yields ``(utt_id, waveform)`` — waveform as the scripts pass it to
+    ``extract_fbank_features`` (float in [-1, 1), shape (N,) or (C, N)) or int16 PCM.  Utterances are
+    grouped into batches of at most ``batch_utterances`` / ``batch_seconds`` of audio, each batch is
+    one fused pass of the CUDA front-end (raw log-mel, no CMVN — the archive holds un-normalised
+    features, :78-84), and every utterance's ``(T, 80)`` float32 matrix is appended to the archive.
+
+    Like the reference's ``_extract`` (:75-88), an utterance that cannot be processed (too short for
+    one 25 ms frame) is reported and gets ``n_frames = 0`` instead of aborting the run.
+
+    :returns: ``(manifest, n_frames, failed)`` — manifest ``{id: "name.zip:offset:size"}``,
+        ``n_frames`` ``{id: T}`` (0 for failures), ``failed`` ``[(id, reason)]``.
+    """
+    from joeys2t_b200 import frontend, tables  # pylint: disable=import-outside-toplevel
+
+    if int(sample_rate) != tables.SAMPLE_RATE:
+        raise ValueError(f"the front-end is specialised for {tables.SAMPLE_RATE} Hz audio")
+    failed: List[Tuple[str, str]] = []
+    n_frames: Dict[str, int] = {}
+    max_samples = int(batch_seconds * sample_rate)
+
+    with ZipFeatureWriter(zip_path) as writer:
+
+        def flush(ids: Sequence[str], waves: Sequence[np.ndarray]):
+            if not ids:
+                return
+            feats, lens = frontend.fbank_cmvn_specaug_ragged(list(waves), layout="ragged")
+            host = feats.cpu().numpy()
+            off = 0
+            for utt_id, t in zip(ids, lens.tolist()):
+                writer.add(utt_id, host[off:off + t])
+                n_frames[utt_id] = t
+                off += t
+
+        ids, waves, total = [], [], 0
+        for utt_id, w in items:
+            arr = np.asarray(w.detach().cpu().numpy() if hasattr(w, "detach") else w)
+            n = int(arr.shape[-1])
+            if tables.num_frames(n) <= 0:
+                failed.append((utt_id, f"waveform of {n} samples is shorter than one 25 ms frame"))
+                n_frames[utt_id] = 0
+                continue
+            if ids and (len(ids) >= batch_utterances or total + n > max_samples):
+                flush(ids, waves)
+                ids, waves, total = [], [], 0
+            ids.append(utt_id)
+            waves.append(arr)
+            total += n
+        flush(ids, waves)
+        manifest = dict(writer.manifest)
+    return manifest, n_frames, failed

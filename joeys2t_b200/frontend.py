@@ -341,6 +341,36 @@ def features_cmvn_specaug_ragged(
 
 
 # ------------------------------------------------------------------------------------------
+# PCM ingest: 48 kHz -> 16 kHz
+# ------------------------------------------------------------------------------------------
+def reformat_48k_to_16k(y: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Device-side ``reformat_freq`` for ``sr == 48000`` (``scripts/gradio_demo.py:35-45``):
+    ``((y / max(max(y), 1)) * 32767).reshape(-1, 3).mean(1).astype(int16)`` — bit-identical to
+    numpy (float64 arithmetic for int16 input, float32 for float32 input).
+
+    :param y: 1-D CUDA tensor, int16 or float32, length divisible by 3
+    :returns: int16 CUDA tensor of length ``len(y) // 3``
+    """
+    _require_cuda()
+    if not y.is_cuda or y.dim() != 1 or y.dtype not in (torch.int16, torch.float32):
+        raise ValueError("reformat_48k_to_16k needs a 1-D CUDA tensor of int16 or float32 samples")
+    n = y.numel()
+    if n % 3 != 0:
+        raise ValueError(f"cannot reshape array of size {n} into shape (-1, 3)")
+    y = y.contiguous()
+    ctx = get_context(y.device.index)
+    if out is None:
+        out = torch.empty(n // 3, dtype=torch.int16, device=y.device)
+    ws = torch.empty(2, dtype=torch.int32, device=y.device)
+    lib = _lib.load()
+    with torch.cuda.device(y.device):
+        _lib.check(lib.js2t_reformat_48k_to_16k(
+            ctx.handle, y.data_ptr(), int(y.dtype == torch.float32), n, out.data_ptr(),
+            ws.data_ptr(), _stream_ptr()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------
 # host-resident streaming: H2D, kernels and D2H of consecutive batches overlap
 # ------------------------------------------------------------------------------------------
 class HostPipeline:

@@ -138,6 +138,29 @@ def load_waveform(path: Path) -> Tuple[np.ndarray, int]:
     return waveform.numpy(), sample_rate
 
 
+def reformat_freq(sr: int, y: np.ndarray) -> Tuple[np.ndarray, int]:
+    """48 kHz → 16 kHz PCM ingest of the demo front door — ``scripts/gradio_demo.py:35-45``, same
+    name, arguments and results: anything but 48 kHz / 16 kHz raises ``ValueError("Unsupported
+    rate", sr)``; 48 kHz audio is peak-normalised, averaged in blocks of three and truncated to
+    int16 on the GPU (bit-identical to the numpy expression); 16 kHz audio passes through.
+
+    Deviation: the device path takes int16 or float32 samples (what microphones / decoders hand
+    over); other dtypes raise instead of silently running on the CPU.
+    """
+    if sr not in (48000, 16000):  # we convert 48k -> 16k
+        raise ValueError("Unsupported rate", sr)
+    if sr == 48000:
+        arr = np.asarray(y)
+        if arr.dtype not in (np.int16, np.float32):
+            raise ValueError(f"reformat_freq: int16 or float32 samples expected, got {arr.dtype}")
+        if arr.size % 3 != 0:
+            raise ValueError(f"cannot reshape array of size {arr.size} into shape (-1, 3)")
+        dev = torch.from_numpy(np.ascontiguousarray(arr).reshape(-1)).cuda()
+        y = frontend.reformat_48k_to_16k(dev).cpu().numpy()
+        sr = 16000
+    return y, sr
+
+
 def get_features(root_path: Path, fbank_path: str) -> np.ndarray:
     """Get speech features from a wav/mp3, a .npy, or a ZIP file accessed via byte offset and
     length — helpers_for_audio.py:100-127.
