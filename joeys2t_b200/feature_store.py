@@ -125,17 +125,18 @@ class ZipFeatureWriter:
 def extract_corpus(
     items: Iterable[Tuple[str, "np.ndarray"]],
     zip_path: Path,
-    batch_utterances: int = 256,
-    batch_seconds: float = 4000.0,
+    batch_utterances: int = 64,
+    batch_seconds: float = 1000.0,
     sample_rate: int = 16000,
 ) -> Tuple[Dict[str, str], Dict[str, int], List[Tuple[str, str]]]:
     """GPU replacement of the prep scripts' extraction loop (``prepare_librispeech.py:74-107``).
 
     ``items`` yields ``(utt_id, waveform)`` — waveform as the scripts pass it to
     ``extract_fbank_features`` (float in [-1, 1), shape (N,) or (C, N)) or int16 PCM.  Utterances are
-    grouped into batches of at most ``batch_utterances`` / ``batch_seconds`` of audio, each batch is
+    grouped into batches of at most ``batch_utterances`` / ``batch_seconds`` of audio; each batch is
     one fused pass of the CUDA front-end (raw log-mel, no CMVN — the archive holds un-normalised
-    features, :78-84), and every utterance's ``(T, 80)`` float32 matrix is appended to the archive.
+    features, :78-84) through :class:`joeys2t_b200.frontend.HostPipeline`, so the H2D copy and the
+    kernels of batch ``i + 1`` run while batch ``i`` is serialised into the archive.
 
     Like the reference's ``_extract`` (:75-88), an utterance that cannot be processed (too short for
     one 25 ms frame) is reported and gets ``n_frames = 0`` instead of aborting the run.
@@ -143,6 +144,8 @@ def extract_corpus(
     :returns: ``(manifest, n_frames, failed)`` — manifest ``{id: "name.zip:offset:size"}``,
         ``n_frames`` ``{id: T}`` (0 for failures), ``failed`` ``[(id, reason)]``.
     """
+    import torch  # pylint: disable=import-outside-toplevel
+
     from joeys2t_b200 import frontend, tables  # pylint: disable=import-outside-toplevel
 
     if int(sample_rate) != tables.SAMPLE_RATE:
@@ -150,19 +153,34 @@ def extract_corpus(
     failed: List[Tuple[str, str]] = []
     n_frames: Dict[str, int] = {}
     max_samples = int(batch_seconds * sample_rate)
+    n_slots = 2
+    max_pcm_bytes = max_samples * 4 + 16 * batch_utterances
+    max_rows = max_samples // tables.FRAME_SHIFT + batch_utterances
+    pipe = frontend.HostPipeline(n_slots, max_pcm_bytes, max_rows)
+    stage = [torch.empty(max_pcm_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(n_slots)]
 
     with ZipFeatureWriter(zip_path) as writer:
+        pending = []  # (slot, ids, plan) in flight
 
-        def flush(ids: Sequence[str], waves: Sequence[np.ndarray]):
+        def drain(keep: int):
+            while len(pending) > keep:
+                slot, ids, plan = pending.pop(0)
+                host = pipe.result(slot).numpy()
+                off = 0
+                for utt_id, t in zip(ids, plan.n_frames.tolist()):
+                    writer.add(utt_id, host[off:off + t])
+                    n_frames[utt_id] = t
+                    off += t
+                plan.close()
+
+        def submit(ids: Sequence[str], waves: Sequence[np.ndarray]):
             if not ids:
                 return
-            feats, lens = frontend.fbank_cmvn_specaug_ragged(list(waves), layout="ragged")
-            host = feats.cpu().numpy()
-            off = 0
-            for utt_id, t in zip(ids, lens.tolist()):
-                writer.add(utt_id, host[off:off + t])
-                n_frames[utt_id] = t
-                off += t
+            drain(n_slots - 1)  # the slot about to be reused has been written out
+            j = pipe._next  # pylint: disable=protected-access
+            packed = frontend.PackedPCM(list(waves), host=stage[j])
+            plan = frontend.Plan(packed.n_samples, packed.byte_off, packed.is_f32)
+            pending.append((pipe.submit(packed, plan), list(ids), plan))
 
         ids, waves, total = [], [], 0
         for utt_id, w in items:
@@ -172,12 +190,16 @@ def extract_corpus(
                 failed.append((utt_id, f"waveform of {n} samples is shorter than one 25 ms frame"))
                 n_frames[utt_id] = 0
                 continue
+            if n > max_samples:
+                raise ValueError(f"{utt_id}: {n / sample_rate:.0f} s of audio exceeds batch_seconds")
             if ids and (len(ids) >= batch_utterances or total + n > max_samples):
-                flush(ids, waves)
+                submit(ids, waves)
                 ids, waves, total = [], [], 0
             ids.append(utt_id)
             waves.append(arr)
             total += n
-        flush(ids, waves)
+        submit(ids, waves)
+        drain(0)
+        pipe.synchronize()
         manifest = dict(writer.manifest)
     return manifest, n_frames, failed

@@ -87,7 +87,9 @@ def _as_1d_pcm(w: Array) -> np.ndarray:
 class PackedPCM:
     """Ragged batch packed into one pinned byte buffer, every utterance 16-byte aligned."""
 
-    def __init__(self, waveforms: Sequence[Array]):
+    def __init__(self, waveforms: Sequence[Array], host: Optional[torch.Tensor] = None):
+        """:param host: optional pinned uint8 tensor to pack into (reused staging buffer of a
+            streaming caller); must be large enough"""
         arrs = [_as_1d_pcm(w) for w in waveforms]
         self.n_samples = np.array([a.shape[0] for a in arrs], np.int64)
         self.is_f32 = np.array([a.dtype != np.int16 for a in arrs], np.uint8)
@@ -95,8 +97,13 @@ class PackedPCM:
         aligned = (sizes + 15) // 16 * 16
         self.byte_off = np.concatenate([[0], np.cumsum(aligned)[:-1]]).astype(np.int64)
         self.nbytes = int(aligned.sum())
-        pin = torch.cuda.is_available()
-        self.host = torch.empty(max(self.nbytes, 16), dtype=torch.uint8, pin_memory=pin)
+        if host is not None:
+            if host.dtype != torch.uint8 or host.numel() < self.nbytes:
+                raise ValueError(f"staging buffer too small: {host.numel()} < {self.nbytes} bytes")
+            self.host = host
+        else:
+            pin = torch.cuda.is_available()
+            self.host = torch.empty(max(self.nbytes, 16), dtype=torch.uint8, pin_memory=pin)
         hv = self.host.numpy()
         for a, o in zip(arrs, self.byte_off):
             hv[o:o + a.nbytes] = a.view(np.uint8)
