@@ -251,11 +251,15 @@ def run_reference(args):
     sample = cpu_sample(waves, cores)
     hours = sum(len(w) for w in sample) / SR / 3600.0
     import multiprocessing as mp
+    # one thread per worker process (the workers import torch after the fork and inherit this):
+    # without it every worker spins up its own OpenMP / MKL pool and the cores are oversubscribed
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("MKL_NUM_THREADS", "1")
     ctx = mp.get_context("fork")
     times = []
     with ctx.Pool(cores, initializer=_cpu_init) as pool:
         for _ in range(max(args.warmup, 1)):
-            pool.map(_cpu_worker, sample[:cores])
+            pool.map(_cpu_worker, sample, chunksize=1)
         # keep the whole run within a few minutes
         steps = args.steps
         t_all = time.perf_counter()
