@@ -307,6 +307,9 @@ def run_b200(args):
     rank, local_rank, world = distributed.init_from_env()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # host thread (and the pinned buffers it first-touches) next to the GPU: the e2e path is PCIe-bound
+    orig_affinity = os.sched_getaffinity(0)
+    numa_bound = frontend.bind_host_thread_to_gpu(local_rank) if not os.environ.get("JS2T_NO_NUMA_BIND") else False
     if _lib.is_stale():
         if local_rank == 0:
             _lib.build()
@@ -458,8 +461,10 @@ def run_b200(args):
         }
         if e2e:
             line["e2e"] = {"value": hours_all / (e2e_ms_max * 1e-3), "unit": UNIT,
-                           "h2d_bytes_per_step": e2e[2], "d2h_bytes_per_step": e2e[3]}
+                           "h2d_bytes_per_step": e2e[2], "d2h_bytes_per_step": e2e[3],
+                           "host_thread_bound_to_gpu_numa_node": bool(numa_bound)}
         if not args.no_cpu_baseline and world == 1:
+            os.sched_setaffinity(0, orig_affinity)  # the CPU baseline gets every core back
             cores = os.cpu_count() or 1
             sample = cpu_sample(batches[0], cores)
             v, dt, passes = cpu_port_throughput(sample, cores)

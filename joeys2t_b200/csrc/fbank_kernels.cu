@@ -27,6 +27,8 @@
 
 #include <string.h>
 
+#include <utility>
+
 #include "mel_structure.inc"
 
 namespace js2t {
@@ -237,6 +239,27 @@ __device__ __forceinline__ int4 ldg_stream_int4(const void* p) {
   return r;
 }
 
+// Raw log-mel rows that a second kernel (apply) reads back.  The PCM that streams through is marked
+// evict-first (tma_load_1d), which is what keeps these rows in L2; additionally marking the rows
+// evict-last (-DJS2T_OUT_EVICT_LAST=1) gained only 0.6 us per config-2 step and leaves sticky lines
+// behind for whatever runs next, so plain stores are the default.
+#ifndef JS2T_OUT_EVICT_LAST
+#define JS2T_OUT_EVICT_LAST 0
+#endif
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_keep(float* p, float v, unsigned long long pol) {
+#if JS2T_OUT_EVICT_LAST
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+#else
+  (void)pol;
+  *p = v;
+#endif
+}
+
 // ---- mel stage: one run of consecutive filters [M0, M1), lane = frame ---------------------------------
 // FFT bins a run of filters needs: segments M0..M1 of the two-band structure (mel_structure.inc)
 __host__ __device__ constexpr int mel_bin_lo(int m0, int m1) {
@@ -287,6 +310,25 @@ __device__ __forceinline__ void mel_group(const float* __restrict__ Pl, float* _
 //  tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the int16 PCM of the *next* tile is fetched by one
 //  bulk async copy (cp.async.bulk, TMA 1-D) into shared memory while the current tile is computed.
 // =====================================================================================================
+// Programmatic dependent launch (-DJS2T_PDL=0 disables): the three kernels of a step are launched
+// with programmatic stream serialization, so the next grid is scheduled — and runs its prologue — while
+// the previous one drains, instead of paying a full launch latency at every kernel boundary.
+//   pdl_wait()   everything the preceding grid wrote is visible after this (no-op otherwise)
+//   pdl_launch() the dependent grid may be scheduled once every CTA of this grid got here or exited
+#ifndef JS2T_PDL
+#define JS2T_PDL 1
+#endif
+__device__ __forceinline__ void pdl_wait() {
+#if JS2T_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_launch() {
+#if JS2T_PDL
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
   return (unsigned)__cvta_generic_to_shared(p);
 }
@@ -312,11 +354,26 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
+#ifndef JS2T_PCM_EVICT_FIRST
+#define JS2T_PCM_EVICT_FIRST 1
+#endif
+#if JS2T_PCM_EVICT_FIRST
+  // PCM is read exactly once: mark its lines evict-first so that the 126 MB L2 keeps the freshly
+  // written log-mel rows instead, which the apply kernel reads back (newest tiles first)
+  unsigned long long policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+#else
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
           smem_u32(dst)),
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
+#endif
 }
 
 // PCM slots a tile occupies: none (pure padding), one (int16, or fp32 with <= 16 frames), two (fp32)
@@ -437,6 +494,12 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
   __shared__ int sMaskTab[kMode == kModeNormKnown ? 2 * kMaxEpilogueMasks : 1];  // this tile's utterance
   __shared__ float sMaskVal;
   __shared__ unsigned sTileMask[4];  // per tile: masked rows | masked columns (3 words), see the epilogue
+  pdl_launch();  // every CTA of this persistent grid is resident: dependents only fill SMs we have left
+  // The preceding grid must be complete before the first claim (back-to-back launches of this kernel
+  // on one plan share the scheduler counters), the first global write and, in mode 2, the statistics
+  // read.  What overlaps its tail is the launch itself and the table / barrier set-up above.  (Claiming
+  // and prefetching the first tile before the wait, where that is safe, gained nothing measurable.)
+  pdl_wait();
   if (kMode == kModeNormKnown && tid < 2 * kMel) sGN[tid] = tid < kMel ? p.g_mean[tid] : p.g_istd[tid - kMel];
   __syncthreads();
 
@@ -482,6 +545,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
   unsigned kslot = 0;
 
   if (is_sched && cur.nf > 0) prefetch_tile(p, cur, sRaw, sBar, 0);
+
 
   while (true) {
     JS2T_WSTAMP(0)
@@ -767,6 +831,8 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
 #endif
         } else if (kMode != kModeNormKnown || JS2T_TEST_EPI == 1) {
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
+          // rows that the apply kernel reads back stay in L2; final rows (no CMVN) need no hint
+          const unsigned long long keep = l2_policy_evict_last();
           if (nf == kTileFrames) {
             // full tile (all but the last tile of an utterance): no row predicates, loads first
             const float* src = sOut + 4 * warp * kOutStride + lane;
@@ -780,9 +846,9 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              dst[i * kMel] = x[3 * i];
-              dst[i * kMel + 32] = x[3 * i + 1];
-              if (c2ok) dst[i * kMel + 64] = x[3 * i + 2];
+              st_keep(dst + i * kMel, x[3 * i], keep);
+              st_keep(dst + i * kMel + 32, x[3 * i + 1], keep);
+              if (c2ok) st_keep(dst + i * kMel + 64, x[3 * i + 2], keep);
             }
             if (p.tile_stats != nullptr) {
 #pragma unroll
@@ -804,9 +870,9 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
                 const float x0 = valid ? src[0] : p.pad_value;
                 const float x1 = valid ? src[32] : p.pad_value;
                 const float x2 = (valid && c2ok) ? src[64] : p.pad_value;
-                dst[0] = x0;
-                dst[32] = x1;
-                if (c2ok) dst[64] = x2;
+                st_keep(dst, x0, keep);
+                st_keep(dst + 32, x1, keep);
+                if (c2ok) st_keep(dst + 64, x2, keep);
                 if (valid) {
                   s0 += x0; q0 = fmaf(x0, x0, q0);
                   s1 += x1; q1 = fmaf(x1, x1, q1);
@@ -898,6 +964,8 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
 //  SpecAugment can run on feature matrices that did not come from the fbank kernel.
 // =====================================================================================================
 __global__ void __launch_bounds__(kThreads) feature_tile_kernel(const FbankLaunch p) {
+  pdl_launch();
+  pdl_wait();
   const TileDesc td = p.tiles[blockIdx.x];
   const int nf = td.nf;
   const int rows = td.rows;
@@ -923,20 +991,34 @@ __global__ void __launch_bounds__(kThreads) feature_tile_kernel(const FbankLaunc
 //  Kernel F: per-utterance statistics -> mean / inverse std / SpecAugment fill value
 //  (joeynmt/data_augmentation.py:96-109 CMVN; :43-46 mask value; tokenizers.py:488-493 order)
 // =====================================================================================================
-constexpr int kFinalizeThreads = 192;
+constexpr int kFinalizeParts = 4;
+constexpr int kFinalizeThreads = kFinalizeParts * kStatsPerTile;  // 640
 __global__ void __launch_bounds__(kFinalizeThreads) finalize_utt_kernel(const FinalizeLaunch p) {
   const int u = blockIdx.x;
   const int b = threadIdx.x;  // mel bin (threads >= 80 only help with the column sums)
-  const UttDesc ud = p.utts[u];
+  pdl_launch();
+  const UttDesc ud = p.utts[u];  // plan data, not produced by the preceding grid
+  pdl_wait();                    // the per-tile statistics (and raw rows) are complete and visible
   const int T = ud.n_frames;
   const int n_tiles = (T + kTileFrames - 1) / kTileFrames;
   __shared__ double s_red[kMel];
+  __shared__ double s_part[kFinalizeParts][kStatsPerTile];
   __shared__ double s_col[kStatsPerTile];
   __shared__ float s_mv;
 
-  if (b < kStatsPerTile) {  // one thread per statistics column: sums and sums of squares side by side
-    const float* ts = p.tile_stats + (long long)ud.tile_start * kStatsPerTile;
-    const double acc = sum_tile_column(ts + b, n_tiles);  // fixed order: deterministic
+  {
+    // four threads per statistics column (sums and sums of squares side by side), each over a fixed
+    // contiguous quarter of the utterance's tiles in tile order, combined in a fixed order:
+    // deterministic, and the kernel (pure L2 latency) has four times the loads in flight
+    const int col = b % kStatsPerTile, part = b / kStatsPerTile;
+    const int per = (n_tiles + kFinalizeParts - 1) / kFinalizeParts;
+    const int lo = min(part * per, n_tiles), hi = min(lo + per, n_tiles);
+    const float* ts = p.tile_stats + ((long long)ud.tile_start + lo) * kStatsPerTile;
+    s_part[part][col] = sum_tile_column(ts + col, hi - lo);
+  }
+  __syncthreads();
+  if (b < kStatsPerTile) {
+    const double acc = (s_part[0][b] + s_part[1][b]) + (s_part[2][b] + s_part[3][b]);
     s_col[b] = acc;
     if (p.stats_out != nullptr) p.stats_out[(long long)u * kStatsPerTile + b] = acc;
   }
@@ -1034,109 +1116,74 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_utt_kernel(const Fi
 // =====================================================================================================
 //  Kernel C: in-place CMVN + SpecAugment fill (+ padding rows of the padded layout)
 // =====================================================================================================
-// Each CTA normalises kApplyTiles consecutive tiles.  The kernel is a pure stream (read 320 B, write
-// 320 B per frame, mostly L2 hits right after the fbank kernel) and therefore bound by the bytes in
-// flight per SM: every thread issues all of its 16-byte loads (up to 3 per tile) before the first use.
-#ifndef JS2T_APPLY_TILES
-#define JS2T_APPLY_TILES 1
-#endif
-constexpr int kApplyTiles = JS2T_APPLY_TILES;
-constexpr int kApplyVec = (kTileFrames * (kMel / 4) + kThreads - 1) / kThreads;  // float4 per thread per tile = 3
+// One CTA per tile, 320 threads = 16 rows x 20 float4 columns; every thread owns ONE float4 column of
+// rows r and r + 16, so the per-column state (mean, 1/std, the four frequency-mask bits) is loaded /
+// derived once per thread and the per-element work is four FMAs and a select.  No shared memory, no
+// barrier; both 16-byte loads are issued before anything else.  The kernel is a pure stream (read
+// 320 B, write 320 B per frame).  Tiles are visited newest first: the fbank kernel wrote them in
+// ascending order just before (its PCM reads are marked evict-first), so the highest-numbered tiles
+// are still dirty in L2 — they hit in cache and are overwritten before the raw values ever reach HBM.
+constexpr int kApplyThreads = 320;
+static_assert(kApplyThreads == (kTileFrames / 2) * (kMel / 4), "16 rows x 20 float4 columns");
 
-__global__ void __launch_bounds__(kThreads) apply_kernel(const ApplyLaunch p) {
-  const int tile0 = blockIdx.x * kApplyTiles;
-  const int n_masks = p.n_fmask + p.n_tmask;
-  __shared__ unsigned sMask[kApplyTiles][4];  // per tile: masked rows | masked columns (3 words)
+__global__ void __launch_bounds__(kApplyThreads) apply_kernel(const ApplyLaunch p) {
+  const int tile = (int)(gridDim.x - 1 - blockIdx.x);
+  pdl_launch();
+  const TileDesc td = p.tiles[tile];  // plan data, not produced by the preceding grid
+  const int c4 = threadIdx.x % (kMel / 4), r = threadIdx.x / (kMel / 4);  // column 0..19, row 0..15
+  pdl_wait();  // mean / 1/std / fill values of the finalize kernel (and, through it, the raw rows)
+  const int nf = td.nf, rows = td.rows;
+  float4* o4 = reinterpret_cast<float4*>(p.out + td.out_row0 * (long long)kMel) + c4;
+  const bool v0 = r < nf, v1 = r + 16 < nf;
+  float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+  if (v0) x0 = o4[r * (kMel / 4)];
+  if (v1) x1 = o4[(r + 16) * (kMel / 4)];
 
-  // the utterance's mask table -> bit masks of each tile (warp j handles tile j)
-  if (threadIdx.x < 32 * kApplyTiles) {
-    const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    bool trow = false, c0 = false, c1 = false, c2 = false;
-    if (p.masks != nullptr && tile0 + j < p.n_tiles) {
-      const TileDesc td = p.tiles[tile0 + j];
-      const int* mk = p.masks + (long long)td.utt * n_masks * 2;
-      for (int i = 0; i < p.n_fmask; ++i) {
-        const int f0 = mk[2 * i];
-        const unsigned w = (unsigned)mk[2 * i + 1];
-        c0 |= (unsigned)(lane - f0) < w;
-        c1 |= (unsigned)(lane + 32 - f0) < w;
-        c2 |= (unsigned)(lane + 64 - f0) < w;
-      }
-      for (int i = p.n_fmask; i < n_masks; ++i)
-        trow |= (unsigned)(td.frame0 + lane - mk[2 * i]) < (unsigned)mk[2 * i + 1];
+  const long long so = p.shared_stats ? 0 : (long long)td.utt * kMel;
+  const float4 mu = __ldg(reinterpret_cast<const float4*>(p.mean + so) + c4);
+  const float4 is = __ldg(reinterpret_cast<const float4*>(p.istd + so) + c4);
+  // this thread's four frequency-mask bits and the time-mask bit of each of its two rows
+  unsigned cm = 0;
+  bool t0 = false, t1 = false;
+  float mv = 0.f;
+  if (p.masks != nullptr) {
+    const int n_masks = p.n_fmask + p.n_tmask;
+    const int* mk = p.masks + (long long)td.utt * n_masks * 2;
+    for (int i = 0; i < p.n_fmask; ++i) {
+      const int f0 = __ldg(mk + 2 * i);
+      const unsigned w = (unsigned)__ldg(mk + 2 * i + 1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cm |= (unsigned)((unsigned)(4 * c4 + j - f0) < w) << j;
     }
-    const unsigned b0 = __ballot_sync(0xffffffffu, trow), b1 = __ballot_sync(0xffffffffu, c0),
-                   b2 = __ballot_sync(0xffffffffu, c1), b3 = __ballot_sync(0xffffffffu, c2);
-    if (lane == 0) {
-      sMask[j][0] = b0;
-      sMask[j][1] = b1;
-      sMask[j][2] = b2;
-      sMask[j][3] = b3;
+    for (int i = p.n_fmask; i < n_masks; ++i) {
+      const int s0 = __ldg(mk + 2 * i);
+      const unsigned w = (unsigned)__ldg(mk + 2 * i + 1);
+      t0 |= (unsigned)(td.frame0 + r - s0) < w;
+      t1 |= (unsigned)(td.frame0 + r + 16 - s0) < w;
     }
+    mv = __ldg(p.mask_value + td.utt);
   }
-
-  // issue every load of this thread first
-  float4 x[kApplyTiles][kApplyVec];
-  int nfv[kApplyTiles], rowsv[kApplyTiles], uttv[kApplyTiles];
-  float4* o4v[kApplyTiles];
-#pragma unroll
-  for (int j = 0; j < kApplyTiles; ++j) {
-    nfv[j] = rowsv[j] = uttv[j] = 0;
-    o4v[j] = nullptr;
-    if (tile0 + j < p.n_tiles) {
-      const TileDesc td = p.tiles[tile0 + j];
-      nfv[j] = td.nf;
-      rowsv[j] = td.rows;
-      uttv[j] = td.utt;
-      o4v[j] = reinterpret_cast<float4*>(p.out + td.out_row0 * (long long)kMel);
-#pragma unroll
-      for (int v = 0; v < kApplyVec; ++v) {
-        const int e = threadIdx.x + v * kThreads;
-        if (e < nfv[j] * (kMel / 4)) x[j][v] = o4v[j][e];
-      }
+  const float4 pad = make_float4(p.pad_value, p.pad_value, p.pad_value, p.pad_value);
+  const bool after = p.cmvn_after != 0;
+  auto norm = [&](float4 x, bool trow) {
+    const unsigned m = trow ? 0xfu : cm;
+    if (after) {  // SpecAugment saw the raw log-mel; CMVN normalises the filled cells too
+      if (m & 1u) x.x = mv;
+      if (m & 2u) x.y = mv;
+      if (m & 4u) x.z = mv;
+      if (m & 8u) x.w = mv;
     }
-  }
-  __syncthreads();
-
-#pragma unroll
-  for (int j = 0; j < kApplyTiles; ++j) {
-    if (o4v[j] == nullptr) continue;
-    const long long so = p.shared_stats ? 0 : (long long)uttv[j] * kMel;
-    const float4* mean4 = reinterpret_cast<const float4*>(p.mean + so);
-    const float4* istd4 = reinterpret_cast<const float4*>(p.istd + so);
-    const float mv = (p.mask_value != nullptr) ? p.mask_value[uttv[j]] : 0.f;
-    const unsigned rowm = sMask[j][0];
-#pragma unroll
-    for (int v = 0; v < kApplyVec; ++v) {
-      const int e = threadIdx.x + v * kThreads;
-      if (e >= rowsv[j] * (kMel / 4)) continue;
-      const int f = e / (kMel / 4), c4 = e - f * (kMel / 4);
-      float4 y;
-      if (f < nfv[j]) {
-        float4 xx = x[j][v];
-        const float4 mu = mean4[c4], is = istd4[c4];
-        // four column bits of this float4 (never straddle a word) | the row bit
-        unsigned m = (sMask[j][1 + (c4 >> 3)] >> ((4 * c4) & 31)) & 0xfu;
-        if ((rowm >> f) & 1u) m = 0xfu;
-        if (p.cmvn_after) {  // SpecAugment saw the raw log-mel; CMVN normalises the filled cells too
-          if (m & 1u) xx.x = mv;
-          if (m & 2u) xx.y = mv;
-          if (m & 4u) xx.z = mv;
-          if (m & 8u) xx.w = mv;
-        }
-        y = make_float4((xx.x - mu.x) * is.x, (xx.y - mu.y) * is.y, (xx.z - mu.z) * is.z, (xx.w - mu.w) * is.w);
-        if (!p.cmvn_after) {
-          if (m & 1u) y.x = mv;
-          if (m & 2u) y.y = mv;
-          if (m & 4u) y.z = mv;
-          if (m & 8u) y.w = mv;
-        }
-      } else {
-        y = make_float4(p.pad_value, p.pad_value, p.pad_value, p.pad_value);
-      }
-      o4v[j][e] = y;
+    float4 y = make_float4((x.x - mu.x) * is.x, (x.y - mu.y) * is.y, (x.z - mu.z) * is.z, (x.w - mu.w) * is.w);
+    if (!after) {
+      if (m & 1u) y.x = mv;
+      if (m & 2u) y.y = mv;
+      if (m & 4u) y.z = mv;
+      if (m & 8u) y.w = mv;
     }
-  }
+    return y;
+  };
+  if (r < rows) o4[r * (kMel / 4)] = v0 ? norm(x0, t0) : pad;
+  if (r + 16 < rows) o4[(r + 16) * (kMel / 4)] = v1 ? norm(x1, t1) : pad;
 }
 
 // =====================================================================================================
@@ -1222,34 +1269,46 @@ int fbank_persistent_grid() {
   return g_fbank_grid;
 }
 
+// launch with programmatic stream serialization (see pdl_wait / pdl_launch)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = JS2T_PDL ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 cudaError_t launch_fbank(const FbankLaunch& p, cudaStream_t s) {
   if (p.n_tiles <= 0) return cudaSuccess;
   int full = fbank_persistent_grid();
   if (p.grid_limit > 0 && p.grid_limit < full) full = p.grid_limit;  // tuning only (option "max_ctas")
   const int grid = p.n_tiles < full ? p.n_tiles : full;
   if (p.epilogue == kEpiNormKnown)
-    fbank_tile_kernel<kModeNormKnown><<<grid, kThreads, kSmemBytes, s>>>(p);
-  else
-    fbank_tile_kernel<kModeRaw><<<grid, kThreads, kSmemBytes, s>>>(p);
-  return cudaGetLastError();
+    return launch_pdl(fbank_tile_kernel<kModeNormKnown>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
+  return launch_pdl(fbank_tile_kernel<kModeRaw>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
 }
 
 cudaError_t launch_features(const FbankLaunch& p, cudaStream_t s) {
   if (p.n_tiles <= 0) return cudaSuccess;
-  feature_tile_kernel<<<p.n_tiles, kThreads, 0, s>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(feature_tile_kernel, dim3(p.n_tiles), dim3(kThreads), 0, s, p);
 }
 
 cudaError_t launch_finalize(const FinalizeLaunch& p, cudaStream_t s) {
   if (p.n_utts <= 0) return cudaSuccess;
-  finalize_utt_kernel<<<p.n_utts, kFinalizeThreads, 0, s>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(finalize_utt_kernel, dim3(p.n_utts), dim3(kFinalizeThreads), 0, s, p);
 }
 
 cudaError_t launch_apply(const ApplyLaunch& p, cudaStream_t s) {
   if (p.n_tiles <= 0) return cudaSuccess;
-  apply_kernel<<<(p.n_tiles + kApplyTiles - 1) / kApplyTiles, kThreads, 0, s>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(apply_kernel, dim3(p.n_tiles), dim3(kApplyThreads), 0, s, p);
 }
 
 cudaError_t launch_global_accumulate(const double* utt_stats, const UttDesc* utts, int n_utts,

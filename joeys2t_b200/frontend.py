@@ -65,6 +65,24 @@ def get_context(device: Optional[int] = None) -> Context:
     return _contexts[device]
 
 
+def bind_host_thread_to_gpu(device: Optional[int] = None) -> bool:
+    """Pin the calling thread to the CPU cores next to ``device`` (NVML's ideal affinity), so that
+    the pinned staging buffers it allocates afterwards are first-touched on the GPU's own NUMA node
+    and host<->device copies do not cross the socket interconnect.  Matters for the host-resident
+    (PCIe-bound) path, mostly with several GPUs per box.  Returns False when NVML is unavailable."""
+    try:
+        import pynvml  # nvidia-ml-py
+        dev = torch.cuda.current_device() if device is None else int(device)
+        pr = torch.cuda.get_device_properties(dev)
+        pynvml.nvmlInit()
+        bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return True
+    except Exception:  # pylint: disable=broad-except
+        return False
+
+
 # ------------------------------------------------------------------------------------------
 # packing
 # ------------------------------------------------------------------------------------------
