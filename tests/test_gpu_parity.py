@@ -574,3 +574,46 @@ def test_mustc_and_longform_full_size_properties(fe):
             assert (err <= 5e-4 + 1e-4 * np.abs(ref[keep])).all()
         else:
             cmvn_close(got, ref)
+
+
+def test_float_pcm_two_slot_path_matches_int16_bit_for_bit(fe):
+    """float32 tiles are staged as two half-tiles (frames 0-15 | 16-31): frame counts around the half
+    and full tile boundaries, int16 and float32 utterances interleaved in one batch — the float path
+    must reproduce the int16 path bit for bit (x / 32768 * 2**15 is exact, quirk Q4)."""
+    rng = np.random.default_rng(11)
+    frames = [1, 2, 15, 16, 17, 18, 31, 32, 33, 47, 48, 49, 64, 65, 100]
+    ints = [rng.integers(-30000, 30000, 400 + 160 * (f - 1) + int(rng.integers(0, 160))).astype(np.int16)
+            for f in frames]
+    floats = [x.astype(np.float32) / np.float32(32768.0) for x in ints]
+    a, nf = fe.fbank_cmvn_specaug_ragged(ints)
+    assert nf.tolist() == frames
+    mixed = [floats[i] if i % 2 == 0 else ints[i] for i in range(len(ints))]
+    mixed2 = [ints[i] if i % 2 == 0 else floats[i] for i in range(len(ints))]
+    for batch in (floats, mixed, mixed2):
+        b, nf2 = fe.fbank_cmvn_specaug_ragged(batch)
+        assert nf2.tolist() == frames and torch.equal(a, b)
+    ref = O.extract_fbank_features(ints[9])
+    off = sum(frames[:9])
+    assert np.abs(a[off:off + frames[9]].cpu().numpy() - ref).max() <= LOGMEL_ATOL
+
+
+def test_non_finite_pcm_does_not_leak_into_other_utterances(fe):
+    """A float utterance full of NaN / Inf poisons only its own rows: what is left in the on-chip PCM
+    slots must never reach the frames of the utterances processed after it (their last frame reads
+    up to 16 samples past the staged data, where the window is zero)."""
+    rng = np.random.default_rng(12)
+    good = [rng.integers(-20000, 20000, n).astype(np.int16) for n in (400, 1999, 5360, 7000, 16000)]
+    good_f = [g.astype(np.float32) / np.float32(32768.0) for g in good]
+    bad = np.full(16000 * 3, np.nan, np.float32)
+    bad[::7] = np.inf
+    clean, nf = fe.fbank_cmvn_specaug_ragged(good + good_f)
+    batch = []
+    for g in good + good_f:
+        batch += [bad, g]
+    out, nf2 = fe.fbank_cmvn_specaug_ragged(batch + [bad] * 40 + good_f)
+    rows = np.concatenate([[0], np.cumsum(nf2)])
+    got = torch.cat([out[rows[2 * i + 1]:rows[2 * i + 2]] for i in range(len(good) * 2)])
+    assert torch.equal(got, clean)
+    tail = out[rows[len(batch) + 40]:]
+    assert torch.equal(tail, clean[sum(nf[:len(good)]):])
+    assert torch.isfinite(clean).all()
