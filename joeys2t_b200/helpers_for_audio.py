@@ -27,12 +27,12 @@ import torch
 from joeys2t_b200 import frontend, tables
 
 
-# from fairseq (kept for API parity; like the reference, its result is not used downstream:
-# helpers_for_audio.py:53-54 overwrites it, and the fbank then reads channel 0)
 def _convert_to_mono(waveform: torch.FloatTensor, sample_rate: int) -> torch.FloatTensor:
-    if waveform.shape[0] > 1:
-        return waveform.mean(0, keepdim=True)
-    return waveform
+    """Down-mix to one channel (API parity with helpers_for_audio.py:21-26).  As in the reference, the
+    result is not what the features are computed from: helpers_for_audio.py:53-54 overwrites it and the
+    fbank then reads channel 0 (quirk Q1)."""
+    del sample_rate  # the reference hands it to sox; a plain mean needs no rate
+    return waveform if waveform.shape[0] <= 1 else waveform.mean(dim=0, keepdim=True)
 
 
 def _check_config(sample_rate: int, n_bins: int):
@@ -66,56 +66,52 @@ def extract_fbank_features(
     n_mel_bins: int = 80,
     overwrite: bool = False
 ) -> Optional[np.ndarray]:
-    """helpers_for_audio.py:41-68.  ``waveform`` is (C, N) in [-1, 1) as returned by
-    ``torchaudio.load`` (int16 PCM tensors/arrays are accepted too and used as they are)."""
-    # pylint: disable=inconsistent-return-statements
-    if output_path is not None and output_path.is_file() and not overwrite:
-        return np.load(output_path.as_posix())
-
+    """Drop-in for helpers_for_audio.py:41-68: (C, N) waveform in [-1, 1) as ``torchaudio.load``
+    returns it (int16 PCM arrays are accepted as they are) -> (T, 80) float32 log-mel on the host.
+    With ``output_path`` the result is cached as ``.npy``: an existing file is returned untouched
+    unless ``overwrite``."""
+    cache = None if output_path is None else Path(output_path)
+    if cache is not None and not overwrite and cache.is_file():
+        return np.load(str(cache))
     try:
         _check_config(sample_rate, n_mel_bins)
-        features, _ = frontend.fbank_cmvn_specaug_ragged([waveform])
-        features = features.cpu().numpy()
-    except Exception as e:
-        stem = output_path.stem if output_path is not None else "<memory>"
-        raise ValueError(
-            f"torchaudio faild to extract mel filterbank features "
-            f"at: {stem}. {e}"
-        ) from e
-
-    if output_path is not None:
-        np.save(output_path.as_posix(), features)
-        assert output_path.is_file(), output_path
-
+        device_feats, _ = frontend.fbank_cmvn_specaug_ragged([waveform])
+    except Exception as err:
+        # the reference's message (helpers_for_audio.py:58-62), also when there is no output path (Q2)
+        where = "<memory>" if cache is None else cache.stem
+        raise ValueError(f"torchaudio faild to extract mel filterbank features at: {where}. {err}") from err
+    features = device_feats.cpu().numpy()
+    if cache is not None:
+        np.save(str(cache), features)
+        if not cache.is_file():
+            raise AssertionError(cache)
     return features
 
 
-# from fairseq
+_NPY_MAGIC = b"\x93N"  # first two bytes of every .npy image (147, 78)
+
+
 def _is_npy_data(data: bytes) -> bool:
-    return data[0] == 147 and data[1] == 78
+    """helpers_for_audio.py:72-73"""
+    return bytes(data[:2]) == _NPY_MAGIC
 
 
-# from fairseq
 def _get_features_from_zip(path, byte_offset, byte_size):
-    with path.open("rb") as f:
-        f.seek(byte_offset)
-        data = f.read(byte_size)
-    byte_features = io.BytesIO(data)
-    if len(data) > 1 and _is_npy_data(data):
-        features = np.load(byte_features)
-    else:
-        raise ValueError(
-            f'Unknown file format for '
-            f'"{path}" [{byte_offset}:{byte_size}]'
-        )
-    return features
+    """One member of an uncompressed zip archive, addressed by raw byte offset and size
+    (helpers_for_audio.py:77-89): the slice must be a ``.npy`` image."""
+    with open(path, "rb") as archive:
+        archive.seek(int(byte_offset))
+        blob = archive.read(int(byte_size))
+    if len(blob) < 2 or not _is_npy_data(blob):
+        raise ValueError(f'Unknown file format for "{path}" [{byte_offset}:{byte_size}]')
+    return np.load(io.BytesIO(blob))
 
 
-# from fairseq
 def get_n_frames(wave_length: int, sample_rate: int):
-    duration_ms = int(wave_length / sample_rate * 1000)
-    n_frames = int(1 + (duration_ms - 25) / 10)
-    return n_frames
+    """helpers_for_audio.py:93-96: frame count estimated from the duration in whole milliseconds
+    (an approximation the reference keeps for manifests; the exact count is ``tables.num_frames``)."""
+    milliseconds = int(1000 * wave_length / sample_rate)
+    return int((milliseconds - 25) / 10 + 1)
 
 
 def load_waveform(path: Path) -> Tuple[np.ndarray, int]:
@@ -162,32 +158,34 @@ def reformat_freq(sr: int, y: np.ndarray) -> Tuple[np.ndarray, int]:
 
 
 def get_features(root_path: Path, fbank_path: str) -> np.ndarray:
-    """Get speech features from a wav/mp3, a .npy, or a ZIP file accessed via byte offset and
-    length — helpers_for_audio.py:100-127.
+    """Speech features of one manifest entry — helpers_for_audio.py:100-127.  ``fbank_path`` is a
+    ``.npy`` file, a ``.wav`` / ``.mp3`` file (features are extracted on the GPU), or
+    ``<archive>.zip:<byte offset>:<byte size>`` pointing into an uncompressed zip of ``.npy`` members.
 
     :return: (np.ndarray) speech features in shape of (num_frames, num_freq)
     """
-    _path, *extra = fbank_path.split(":")
-    _path = Path(root_path) / _path
-    if not _path.is_file():
-        raise FileNotFoundError(f"File not found: {_path}")
+    name, *location = fbank_path.split(":")
+    file = Path(root_path) / name
+    if not file.is_file():
+        raise FileNotFoundError(f"File not found: {file}")
 
-    if len(extra) == 0:
-        if _path.suffix == ".npy":
-            features = np.load(_path.as_posix())
-        elif _path.suffix in [".mp3", ".wav"]:
-            waveform, sample_rate = load_waveform(_path)
-            features = extract_fbank_features(waveform, sample_rate)
+    if not location:
+        kind = file.suffix
+        if kind == ".npy":
+            features = np.load(str(file))
+        elif kind in (".wav", ".mp3"):
+            features = extract_fbank_features(*load_waveform(file))
         else:
-            raise ValueError(f"Invalid file type: {_path}")
-    elif len(extra) == 2:
-        assert _path.suffix == ".zip"
-        extra = [int(i) for i in extra]
-        features = _get_features_from_zip(_path, extra[0], extra[1])
+            raise ValueError(f"Invalid file type: {file}")
+    elif len(location) == 2:
+        if file.suffix != ".zip":
+            raise AssertionError(f"{file}: byte ranges address zip archives")
+        offset, size = (int(v) for v in location)
+        features = _get_features_from_zip(file, offset, size)
     else:
         raise ValueError(f"Invalid path: {root_path / fbank_path}")
 
-    assert len(features.shape) == 2, "spectrogram must be a 2-D array."
+    assert features.ndim == 2, "spectrogram must be a 2-D array."
     return features
 
 
@@ -196,26 +194,19 @@ def pad_features(
     embed_size: int = 80,
     pad_index: int = 1,
 ) -> Tuple[np.ndarray, List[int], None]:
-    """
-    Pad continuous feature representation in batch — helpers_for_audio.py:130-170.
-    Host-side (the inputs are host arrays); the batched device path emits this layout directly
-    (``layout="padded"``), so the collate step has nothing left to copy.
+    """Batch of ragged (T_i, embed_size) matrices -> one (B, max T, embed_size) float32 array filled
+    with ``float(pad_index)`` plus the list of lengths — helpers_for_audio.py:130-170, host side
+    (the inputs are host arrays).  The batched device path writes this layout itself
+    (``layout="padded"``), so a collate step built on it has nothing left to copy.
 
-    :returns:
-      - features np.ndarray, (batch_size, src_len, embed_size) filled with float(pad_index)
-      - lengths List[int], (batch_size)
+    :returns: (features, lengths, None) — the third slot is the reference's unused prompt mask
     """
-    max_len = max([int(f.shape[0]) for f in feat_list])
-    batch_size = len(feat_list)
-    features = np.full((batch_size, max_len, embed_size), float(pad_index), dtype=np.float32)
-    lengths = []
-    for i, f in enumerate(feat_list):
-        length = min(int(f.shape[0]), max_len)
-        assert length > 0, "empty feature!"
-        features[i, :length, :] = f[:length, :]
-        lengths.append(length)
-
-    assert max(lengths) == features.shape[1]
-    assert embed_size == features.shape[2]
-    assert sum(lengths) > 0
+    lengths = [int(np.shape(f)[0]) for f in feat_list]
+    if not lengths or min(lengths) <= 0:
+        raise AssertionError("empty feature!")
+    features = np.full((len(lengths), max(lengths), embed_size), float(pad_index), dtype=np.float32)
+    for row, (feat, length) in enumerate(zip(feat_list, lengths)):
+        if np.shape(feat)[1] != embed_size:
+            raise AssertionError(f"feature width {np.shape(feat)[1]} != embed_size {embed_size}")
+        features[row, :length] = feat
     return features, lengths, None
