@@ -1116,17 +1116,25 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_utt_kernel(const Fi
 // =====================================================================================================
 //  Kernel C: in-place CMVN + SpecAugment fill (+ padding rows of the padded layout)
 // =====================================================================================================
-// One CTA per tile, 320 threads = 16 rows x 20 float4 columns; every thread owns ONE float4 column of
-// rows r and r + 16, so the per-column state (mean, 1/std, the four frequency-mask bits) is loaded /
+// One CTA per tile, 160 threads = 8 rows x 20 float4 columns; every thread owns ONE float4 column of
+// rows r, r + 8, r + 16, r + 24 (config-2 step: 1 row per thread 229.0 us, 2 rows 222.5, 4 rows 219.8,
+// 8 rows 218.5; 4 rows with at least 8 resident CTAs per SM 216.1; register caps beyond that 240+), so the per-column state (mean, 1/std, the four frequency-mask bits) is loaded /
 // derived once per thread and the per-element work is four FMAs and a select.  No shared memory, no
-// barrier; both 16-byte loads are issued before anything else.  The kernel is a pure stream (read
+// barrier; all four 16-byte loads are issued before anything else.  The kernel is a pure stream (read
 // 320 B, write 320 B per frame).  Tiles are visited newest first: the fbank kernel wrote them in
 // ascending order just before (its PCM reads are marked evict-first), so the highest-numbered tiles
 // are still dirty in L2 — they hit in cache and are overwritten before the raw values ever reach HBM.
-constexpr int kApplyThreads = 320;
-static_assert(kApplyThreads == (kTileFrames / 2) * (kMel / 4), "16 rows x 20 float4 columns");
+#ifndef JS2T_APPLY_MIN_CTAS
+#define JS2T_APPLY_MIN_CTAS 8
+#endif
+#ifndef JS2T_APPLY_ROWS
+#define JS2T_APPLY_ROWS 4
+#endif
+constexpr int kApplyRows = JS2T_APPLY_ROWS;                   // rows of the tile per thread
+constexpr int kApplyRowStep = kTileFrames / kApplyRows;       // 8
+constexpr int kApplyThreads = kApplyRowStep * (kMel / 4);     // 160 = 8 rows x 20 float4 columns
 
-__global__ void __launch_bounds__(kApplyThreads) apply_kernel(const ApplyLaunch p) {
+__global__ void __launch_bounds__(kApplyThreads, JS2T_APPLY_MIN_CTAS) apply_kernel(const ApplyLaunch p) {
   const int tile = (int)(gridDim.x - 1 - blockIdx.x);
   pdl_launch();
   const TileDesc td = p.tiles[tile];  // plan data, not produced by the preceding grid
@@ -1134,17 +1142,18 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const ApplyLaunch 
   pdl_wait();  // mean / 1/std / fill values of the finalize kernel (and, through it, the raw rows)
   const int nf = td.nf, rows = td.rows;
   float4* o4 = reinterpret_cast<float4*>(p.out + td.out_row0 * (long long)kMel) + c4;
-  const bool v0 = r < nf, v1 = r + 16 < nf;
-  float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-  if (v0) x0 = o4[r * (kMel / 4)];
-  if (v1) x1 = o4[(r + 16) * (kMel / 4)];
+  float4 x[kApplyRows];
+#pragma unroll
+  for (int i = 0; i < kApplyRows; ++i) {
+    x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r + kApplyRowStep * i < nf) x[i] = o4[(r + kApplyRowStep * i) * (kMel / 4)];
+  }
 
   const long long so = p.shared_stats ? 0 : (long long)td.utt * kMel;
   const float4 mu = __ldg(reinterpret_cast<const float4*>(p.mean + so) + c4);
   const float4 is = __ldg(reinterpret_cast<const float4*>(p.istd + so) + c4);
-  // this thread's four frequency-mask bits and the time-mask bit of each of its two rows
-  unsigned cm = 0;
-  bool t0 = false, t1 = false;
+  // this thread's four frequency-mask bits and the time-mask bit of each of its rows
+  unsigned cm = 0, tm = 0;
   float mv = 0.f;
   if (p.masks != nullptr) {
     const int n_masks = p.n_fmask + p.n_tmask;
@@ -1158,8 +1167,8 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const ApplyLaunch 
     for (int i = p.n_fmask; i < n_masks; ++i) {
       const int s0 = __ldg(mk + 2 * i);
       const unsigned w = (unsigned)__ldg(mk + 2 * i + 1);
-      t0 |= (unsigned)(td.frame0 + r - s0) < w;
-      t1 |= (unsigned)(td.frame0 + r + 16 - s0) < w;
+#pragma unroll
+      for (int k = 0; k < kApplyRows; ++k) tm |= (unsigned)((unsigned)(td.frame0 + r + kApplyRowStep * k - s0) < w) << k;
     }
     mv = __ldg(p.mask_value + td.utt);
   }
@@ -1182,8 +1191,11 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const ApplyLaunch 
     }
     return y;
   };
-  if (r < rows) o4[r * (kMel / 4)] = v0 ? norm(x0, t0) : pad;
-  if (r + 16 < rows) o4[(r + 16) * (kMel / 4)] = v1 ? norm(x1, t1) : pad;
+#pragma unroll
+  for (int i = 0; i < kApplyRows; ++i) {
+    const int f = r + kApplyRowStep * i;
+    if (f < rows) o4[f * (kMel / 4)] = f < nf ? norm(x[i], (tm >> i) & 1u) : pad;
+  }
 }
 
 // =====================================================================================================
