@@ -19,7 +19,7 @@ sys.path.insert(0, str(ROOT))
 from joeys2t_b200 import feature_store, frontend, synthetic  # noqa: E402
 from joeys2t_b200.batching import FrameCountBatchSampler, SpeechBatchCollator  # noqa: E402
 from joeys2t_b200.speech_processor import SpeechProcessor  # noqa: E402
-from oracle import fbank_numpy as O  # noqa: E402  (CPU baseline only)
+from joeys2t_b200 import tables  # noqa: E402
 
 peaks = ROOT / "MEASURED_PEAKS.json"
 hbm = json.loads(peaks.read_text()).get("hbm_gbs", 6650.0) if peaks.is_file() else 6650.0
@@ -62,8 +62,8 @@ for dtype, secs in ((np.int16, 3600), (np.float32, 1800)):
     alg = n * item * 2 + (n // 3) * 2  # the maximum needs its own pass: 2 reads of the input + 1 write
     t0 = time.perf_counter()
     sample = host[: 48000 * 60]
-    with np.errstate(all="ignore"):
-        ref, _ = O.reformat_freq(48000, sample)
+    with np.errstate(all="ignore"):  # the reference's numpy expression (scripts/gradio_demo.py:42-43), timed on one core
+        ref = ((sample / max(np.max(sample), 1)) * 32767).reshape((-1, 3)).mean(axis=1).astype("int16")
     cpu_s = time.perf_counter() - t0
     got = frontend.reformat_48k_to_16k(torch.from_numpy(sample).cuda()).cpu().numpy()
     assert np.array_equal(got, ref)
@@ -76,7 +76,7 @@ for dtype, secs in ((np.int16, 3600), (np.float32, 1800)):
 # ---- f-2 ------------------------------------------------------------------------------------------
 print("\n## f-2  sampler + collator: host int16 PCM -> (B, Tmax, 80) fp32 on the device (utterance CMVN + SpecAugment)")
 waves = synthetic.pooled_batch(256, seed=1234, lo=10.0, hi=15.0)
-n_frames = np.array([O.num_frames(len(w)) for w in waves])
+n_frames = np.array([tables.num_frames(len(w)) for w in waves])
 proc = SpeechProcessor(level="frame", num_freq=80, max_length=3000,
                        specaugment=dict(freq_mask_n=2, freq_mask_f=27, time_mask_n=2, time_mask_t=40, time_mask_p=1.0),
                        cmvn=dict(norm_means=True, norm_vars=True, before=True))
