@@ -509,9 +509,16 @@ def run_b200(args):
 def run_sweep(args, rank, local_rank, world, dev):
     """cfg5: corpus sweep sharded over the ranks with global CMVN whose statistics are NOT known:
     pass 1 = fbank + per-utterance statistics, accumulated on the device in fp64; one all-reduce of
-    161 float64 over NCCL (the path's only collective); pass 2 = fbank with the normalisation fused
-    into the epilogue.  The resident batches are cycled until sweep_hours / world have been processed
-    by this rank in each pass."""
+    161 float64 over NCCL (the path's only collective); pass 2 normalises.  Two strategies for pass 2:
+
+    * retain (default when this rank's share of the features fits in HBM — 115 MB per audio-hour, so
+      1000 h over 8 GPUs is 14 GB each): pass 1 keeps the raw log-mel of the whole share on the device
+      and pass 2 normalises it in place with the apply kernel.  1 280 algorithmic bytes per frame, but
+      the fbank kernel — bound by FP32 issue / latency, not HBM — runs once instead of twice;
+    * recompute (JS2T_SWEEP_RECOMPUTE=1, or the share does not fit): pass 2 runs the fbank kernel
+      again with the normalisation fused into its epilogue: 960 bytes per frame, twice the arithmetic.
+
+    The resident PCM batches are cycled until sweep_hours / world have been processed by this rank."""
     import torch
     import torch.distributed as dist
 
@@ -527,6 +534,18 @@ def run_sweep(args, rank, local_rank, world, dev):
         outs.append(plans[-1].empty_output())
         hours.append(sum(len(w) for w in waves) / SR / 3600.0)
     n_steps = int(np.ceil(args.sweep_hours / world / float(np.mean(hours))))
+    rows = [p.out_rows for p in plans]
+    share_bytes = sum(rows[i % R] for i in range(n_steps)) * 80 * 4
+    free_bytes = torch.cuda.mem_get_info(dev)[0]
+    retain = not os.environ.get("JS2T_SWEEP_RECOMPUTE") and share_bytes < 0.8 * free_bytes
+    store, views = None, []
+    if retain:
+        store = torch.empty(share_bytes // 4, dtype=torch.float32, device=dev)
+        off = 0
+        for i in range(n_steps):
+            n = rows[i % R] * 80
+            views.append(store[off:off + n].view(rows[i % R], 80))
+            off += n
 
     def barrier():
         torch.cuda.synchronize()
@@ -538,15 +557,20 @@ def run_sweep(args, rank, local_rank, world, dev):
         acc = distributed.new_accumulator(dev)
         for p in plans:
             p.set_cmvn("stats")
-        for i in range(n):                                   # pass 1: statistics
-            plans[i % R].execute(pcm_dev[i % R], outs[i % R])
+        for i in range(n):                                   # pass 1: raw log-mel + statistics
+            plans[i % R].execute(pcm_dev[i % R], views[i] if retain else outs[i % R])
             plans[i % R].accumulate_global(acc)
         distributed.allreduce_global_stats(acc)              # the one collective (161 x fp64)
         for p in plans:
             p.finalize_global(acc)
-            p.set_cmvn("global", True, True, True)
-        for i in range(n):                                   # pass 2: normalised features
-            plans[i % R].execute(pcm_dev[i % R], outs[i % R])
+        if retain:
+            for i in range(n):                               # pass 2: normalise the retained rows in place
+                plans[i % R].normalize(views[i])
+        else:
+            for p in plans:
+                p.set_cmvn("global", True, True, True)
+            for i in range(n):                               # pass 2: fbank again, normalised in the epilogue
+                plans[i % R].execute(pcm_dev[i % R], outs[i % R])
         return acc
 
     sweep(max(args.warmup, 3))
@@ -571,22 +595,26 @@ def run_sweep(args, rank, local_rank, world, dev):
         peak, peak_src = measured_peaks()
         ms_max = float(t[0])
         hours_all, frames_all = w.tolist()
-        # 960 B/frame: PCM read twice (2 x 320 B), features written once in pass 2 (320 B); the raw
-        # features pass 1 also writes are not algorithmic traffic
-        achieved = frames_all / world * 960.0 / (ms_max * 1e-3) / 1e9
+        # recompute: 960 B/frame (PCM read twice, features written once; the raw rows pass 1 also writes
+        # are not algorithmic traffic); retain: 1 280 B/frame (PCM in, raw out, raw in, normalised out)
+        bytes_per_frame = 1280.0 if retain else 960.0
+        achieved = frames_all / world * bytes_per_frame / (ms_max * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": hours_all / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": 2 * n_steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / (2 * n_steps),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "baseline_config": "cfg5",
                        "corpus_hours": hours_all, "frames": frames_all, "passes": 2,
+                       "pass2": ("in-place normalisation of the raw log-mel retained in HBM "
+                                 f"({share_bytes / 1e9:.1f} GB per GPU)") if retain
+                                else "fbank recomputed with the normalisation fused into its epilogue",
                        "collective": "one all-reduce (SUM) of 161 float64 between the passes",
                        "global_frames_in_statistics": float(acc[160]),
                        "l2": f"cycling {R} resident batches per GPU (~{R * 204} MB of PCM + features)",
                        "parallelism": f"utterance-sharded x{world}"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
-                         "note": "per GPU; 960 algorithmic bytes per frame for the two-pass global CMVN"},
+                         "note": f"per GPU; {bytes_per_frame:.0f} algorithmic bytes per frame for the two-pass global CMVN"},
             "clocks": clk, "gpu_launches": 4 * n_steps + len(plans),
         }
         print(json.dumps(line), flush=True)

@@ -687,9 +687,13 @@ int js2t_normalize_execute(js2t_plan* plan, float* out_dev, void* stream_) {
   JS2T_CUDA(cudaSetDevice(plan->ctx->device));
   const int saved = plan->cmvn_mode;
   plan->cmvn_mode = JS2T_CMVN_GLOBAL;
-  // per-utterance fill value under the global normalisation (re-reads the per-tile statistics)
-  FinalizeLaunch z = make_finalize(plan, out_dev, /*shared=*/true);
-  cudaError_t e = launch_finalize(z, stream);
+  // per-utterance fill value under the global normalisation (re-reads the per-tile statistics of the
+  // plan's last execute; only SpecAugment needs it)
+  cudaError_t e = cudaSuccess;
+  if (plan->has_masks) {
+    FinalizeLaunch z = make_finalize(plan, out_dev, /*shared=*/true);
+    e = launch_finalize(z, stream);
+  }
   ApplyLaunch a = make_apply(plan, out_dev, /*shared=*/true);
   if (e == cudaSuccess) e = launch_apply(a, stream);
   plan->cmvn_mode = saved;
