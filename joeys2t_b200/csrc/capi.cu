@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -44,7 +45,54 @@ struct js2t_ctx {
   int device = 0;
   float* d_tables = nullptr;  // window_half[400] | tw256[256 x float2] | tw512[136 x float2]
   bool tables_set = false;
+  // Device-buffer pool for plan workspaces: the per-item / per-batch callers of the reference API create
+  // and destroy one plan per call, and cudaMalloc + cudaFree were a third of such a call.
+  std::mutex pool_mu;
+  std::vector<std::pair<size_t, void*>> pool;  // (capacity, pointer) of idle buffers
+  size_t pool_bytes = 0;
 };
+
+namespace {
+
+constexpr size_t kPoolMaxEntries = 16;
+constexpr size_t kPoolMaxBytes = size_t(1) << 30;
+
+// smallest idle buffer that fits without wasting more than 4x, else a fresh allocation (64 KB granules)
+cudaError_t pool_alloc(js2t_ctx* c, size_t bytes, void** out, size_t* cap) {
+  {
+    std::lock_guard<std::mutex> lk(c->pool_mu);
+    size_t best = c->pool.size();
+    for (size_t i = 0; i < c->pool.size(); ++i)
+      if (c->pool[i].first >= bytes && c->pool[i].first <= 4 * bytes + (1 << 20) &&
+          (best == c->pool.size() || c->pool[i].first < c->pool[best].first))
+        best = i;
+    if (best != c->pool.size()) {
+      *cap = c->pool[best].first;
+      *out = c->pool[best].second;
+      c->pool_bytes -= *cap;
+      c->pool.erase(c->pool.begin() + (long)best);
+      return cudaSuccess;
+    }
+  }
+  *cap = align_up(bytes, 64 * 1024);
+  return cudaMalloc(out, *cap);
+}
+
+// The caller guarantees (as with cudaFree) that nothing in flight uses the buffer any more.
+void pool_free(js2t_ctx* c, void* p, size_t cap) {
+  if (p == nullptr) return;
+  {
+    std::lock_guard<std::mutex> lk(c->pool_mu);
+    if (c->pool.size() < kPoolMaxEntries && c->pool_bytes + cap <= kPoolMaxBytes) {
+      c->pool.emplace_back(cap, p);
+      c->pool_bytes += cap;
+      return;
+    }
+  }
+  cudaFree(p);
+}
+
+}  // namespace
 
 struct js2t_plan {
   js2t_ctx* ctx = nullptr;
@@ -55,6 +103,7 @@ struct js2t_plan {
   std::vector<UttDesc> h_utts;
   // device workspace (one allocation)
   void* d_ws = nullptr;
+  size_t ws_cap = 0;
   UttDesc* d_utts = nullptr;
   TileDesc* d_tiles = nullptr;
   float* d_tile_stats = nullptr;
@@ -121,6 +170,7 @@ int js2t_ctx_destroy(js2t_ctx* ctx) {
   if (ctx == nullptr) return JS2T_OK;
   cudaSetDevice(ctx->device);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
+  for (auto& b : ctx->pool) cudaFree(b.second);
   delete ctx;
   return JS2T_OK;
 }
@@ -292,7 +342,7 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
   const size_t o_ustats = carve(sizeof(double) * kStatsPerTile * n_utts);
   const size_t o_sched = carve(sizeof(int) * 2);
   cudaSetDevice(ctx->device);
-  cudaError_t e = cudaMalloc(&p->d_ws, off);
+  cudaError_t e = pool_alloc(ctx, off, &p->d_ws, &p->ws_cap);
   if (e != cudaSuccess) {
     delete p;
     return fail(JS2T_ERR_CUDA, "cudaMalloc(%zu bytes of plan workspace) failed: %s", off, cudaGetErrorString(e));
@@ -313,7 +363,7 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
   if (e == cudaSuccess)
     e = cudaMemcpy(p->d_tiles, tiles.data(), sizeof(TileDesc) * tiles.size(), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
-    cudaFree(p->d_ws);
+    pool_free(ctx, p->d_ws, p->ws_cap);
     delete p;
     return fail(JS2T_ERR_CUDA, "plan descriptor upload failed: %s", cudaGetErrorString(e));
   }
@@ -339,9 +389,11 @@ int js2t_plan_destroy(js2t_plan* plan) {
   if (plan == nullptr) return JS2T_OK;
   cudaSetDevice(plan->ctx->device);
   for (cudaEvent_t e : plan->prof_ev) cudaEventDestroy(e);
-  if (plan->d_masks) cudaFree(plan->d_masks);
+  // like the cudaFree it replaces, destroying a plan waits for whatever still uses its workspace
+  cudaDeviceSynchronize();
+  if (plan->d_masks) pool_free(plan->ctx, plan->d_masks, plan->masks_cap);
   if (plan->d_dbg) cudaFree(plan->d_dbg);
-  if (plan->d_ws) cudaFree(plan->d_ws);
+  if (plan->d_ws) pool_free(plan->ctx, plan->d_ws, plan->ws_cap);
   delete plan;
   return JS2T_OK;
 }
@@ -400,11 +452,17 @@ int js2t_plan_set_masks(js2t_plan* plan, int n_fmask, int n_tmask, const int32_t
   const size_t bytes = sizeof(int32_t) * 2 * (size_t)(n_fmask + n_tmask) * plan->n_utts;
   JS2T_CUDA(cudaSetDevice(plan->ctx->device));
   if (bytes > plan->masks_cap) {
-    if (plan->d_masks) cudaFree(plan->d_masks);
+    if (plan->d_masks) {
+      JS2T_CUDA(cudaDeviceSynchronize());  // an earlier execute may still read the old table
+      pool_free(plan->ctx, plan->d_masks, plan->masks_cap);
+    }
     plan->d_masks = nullptr;
     plan->masks_cap = 0;
-    JS2T_CUDA(cudaMalloc(&plan->d_masks, bytes));
-    plan->masks_cap = bytes;
+    void* m = nullptr;
+    size_t cap = 0;
+    JS2T_CUDA(pool_alloc(plan->ctx, bytes, &m, &cap));
+    plan->d_masks = static_cast<int*>(m);
+    plan->masks_cap = cap;
   }
   JS2T_CUDA(cudaMemcpyAsync(plan->d_masks, table, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
   plan->n_fmask = n_fmask;

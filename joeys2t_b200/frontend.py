@@ -8,6 +8,7 @@ The per-item wrappers with the reference's signatures (``helpers_for_audio.py``,
 ``data_augmentation.py``, ``speech_processor.py``) are batch-of-one calls into this module.
 """
 import ctypes
+import threading
 from typing import List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -288,6 +289,23 @@ class Plan:
 # ------------------------------------------------------------------------------------------
 # one-call batched entry point
 # ------------------------------------------------------------------------------------------
+_tls = threading.local()
+
+
+def _staging(nbytes: int) -> torch.Tensor:
+    """Grow-only pinned staging buffer of the calling thread.  The one-call entry points below
+    synchronise before they return, so the buffer is free again by the next call; allocating pinned
+    memory per call cost more than the kernels for a single utterance."""
+    buf = getattr(_tls, "staging", None)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes * 1.5), 1 << 20), dtype=torch.uint8, pin_memory=True)
+        _tls.staging = buf
+    return buf
+
+
+def _packed_nbytes(waveforms: Sequence[Array]) -> int:
+    return sum((int(np.shape(w)[-1]) * 4 + 15) // 16 * 16 for w in waveforms)  # upper bound (float32)
+
 def fbank_cmvn_specaug_ragged(
     waveforms: Sequence[Array],
     *,
@@ -311,7 +329,8 @@ def fbank_cmvn_specaug_ragged(
         :func:`joeys2t_b200.data_augmentation.draw_masks`)
     :returns: (features on the GPU — ragged ``(sum T, 80)`` or padded ``(B, Tmax, 80)`` —, n_frames)
     """
-    packed = PackedPCM(waveforms)
+    _require_cuda()
+    packed = PackedPCM(waveforms, host=_staging(_packed_nbytes(waveforms)))
     plan = Plan(packed.n_samples, packed.byte_off, packed.is_f32, max_frames=max_frames,
                 layout=layout, pad_value=pad_value)
     if global_stats is not None:
@@ -324,9 +343,10 @@ def fbank_cmvn_specaug_ragged(
                       cmvn.get("before", True))
     if masks is not None:
         plan.set_masks(masks, n_fmask, n_tmask, mask_value)
-    out = plan.execute(packed.to_device(f"cuda:{plan.ctx.device}"))
+    dev_pcm = packed.host[:max(packed.nbytes, 16)].to(f"cuda:{plan.ctx.device}", non_blocking=True)
+    out = plan.execute(dev_pcm)
     n_frames = plan.n_frames.copy()
-    # the plan's workspace must outlive the enqueued kernels
+    # the plan's workspace and the staging buffer must outlive the enqueued copies and kernels
     torch.cuda.current_stream().synchronize()
     plan.close()
     return out, n_frames
