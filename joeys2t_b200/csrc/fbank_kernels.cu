@@ -1048,19 +1048,24 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_utt_kernel(const Fi
         }
       }
     }
-    // fill value = mean of the spectrogram SpecAugment sees (data_augmentation.py:45-46)
-    if (b < kMel) {
-      double col = S / T;                                              // raw column mean
-      if (p.cmvn_enabled && !p.cmvn_after) col = (col - mean) * istd;  // after CMVN(before)
-      s_red[b] = col;
+    // fill value = mean of the spectrogram SpecAugment sees (data_augmentation.py:45-46); nobody reads
+    // it without masks, and the serial 80-term sum below is most of this kernel's critical path
+    if (mk != nullptr) {
+      if (b < kMel) {
+        double col = S / T;                                              // raw column mean
+        if (p.cmvn_enabled && !p.cmvn_after) col = (col - mean) * istd;  // after CMVN(before)
+        s_red[b] = col;
+      }
+      __syncthreads();
+      if (b == 0) {
+        double acc = 0.0;
+        for (int i = 0; i < kMel; ++i) acc += s_red[i];
+        s_mv = (p.mask_value_mode == 1) ? p.mask_value_const : (float)(acc / kMel);
+      }
+      __syncthreads();
+    } else if (b == 0) {
+      s_mv = 0.f;
     }
-    __syncthreads();
-    if (b == 0) {
-      double acc = 0.0;
-      for (int i = 0; i < kMel; ++i) acc += s_red[i];
-      s_mv = (p.mask_value_mode == 1) ? p.mask_value_const : (float)(acc / kMel);
-    }
-    __syncthreads();
   } else {
     // SpecAugment on the raw log-mel first, then CMVN over the *masked* spectrogram
     if (b < kMel) s_red[b] = S / T;
