@@ -74,8 +74,21 @@ __device__ __forceinline__ float log_floor(float x) {
 //   int16 tile  : one slot  = 16 B lead-in + 5360 samples (+ 32 B that row 17 of the last frame pair
 //                 may touch; whatever is there is finite and meets a zero of the window)
 //   fp32 tile   : two slots = frames 0..15 | frames 16..31, each 16 B lead-in + 2816 samples
-constexpr int kSlotBytes = 11296;
+//   full int16 tile (32 frames) : the same slot, but staged as TWO copies — frames 0..15 at the start,
+//                 frames 16..31 (again with their own lead-in) kSplitOff bytes further, where kSplitOff is
+//                 64 mod 128: the lower half-warp of every warp then works on a frame pair of the first
+//                 region and the upper half-warp on one of the second, and the two halves of each row
+//                 load hit disjoint shared-memory banks (one wavefront instead of two)
+#ifndef JS2T_SPLIT_STAGING
+#define JS2T_SPLIT_STAGING 1
+#endif
+constexpr int kSlotBytes = 11392;
+constexpr int kSplitOff = 5696;       // data of the second region relative to the data of the first
+constexpr int kSplitSamples = 2816;   // samples of the first region: frames 0..15 + row 17 of pair (14, 15)
 static_assert(kSlotBytes >= 16 + 2688 * 4 && kSlotBytes >= 16 + 2816 * 4 && kSlotBytes % 16 == 0, "slot size");
+static_assert(kSplitOff % 128 == 64 && kSplitOff >= kSplitSamples * 2 + 16 &&
+                  kSlotBytes >= 16 + kSplitOff + kSplitSamples * 2,
+              "split staging of a full int16 tile");
 constexpr int kExchStride = 17;                   // 8-byte words per row of the 16x16 transpose (padded)
 constexpr int kExchPerWarp = 2 * 16 * kExchStride;   // 8-byte words: two half-warps
 constexpr int kPStride = 34;                      // P[k][frame]: even (64-bit stores), 2k+f banks
@@ -376,6 +389,25 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
 #endif
 }
 
+// same copy without arming the barrier (the caller armed it once for several copies)
+__device__ __forceinline__ void tma_copy_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+#if JS2T_PCM_EVICT_FIRST
+  unsigned long long policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+#else
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+#endif
+}
+
 // PCM slots a tile occupies: none (pure padding), one (int16, or fp32 with <= 16 frames), two (fp32)
 __device__ __forceinline__ int tile_slots(const TileDesc& t) {
   return t.nf == 0 ? 0 : (((t.flags & 1) && t.nf > 16) ? 2 : 1);
@@ -387,7 +419,18 @@ __device__ __forceinline__ void prefetch_tile(const FbankLaunch& p, const TileDe
                                               unsigned long long* bar, unsigned k) {
   const unsigned lead = t.frame0 > 0 ? 16u : 0u;
   const unsigned s0 = k & 1u;
-  if (!(t.flags & 1)) {
+  if (!(t.flags & 1) && t.nf == kTileFrames && JS2T_SPLIT_STAGING) {
+    // full int16 tile: two regions on one barrier (see kSplitOff)
+    unsigned char* slot = sRaw + s0 * kSlotBytes;
+    const unsigned bytes_a = (unsigned)(kSplitSamples * 2) + lead;
+    const unsigned bytes_b = 16u + (unsigned)((kTileSamples - 16 * kHop) * 2);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar + s0)),
+                 "r"(bytes_a + bytes_b)
+                 : "memory");
+    tma_copy_1d(slot + 16 - lead, p.pcm + t.src_byte_off - lead, bytes_a, bar + s0);
+    tma_copy_1d(slot + kSplitOff, p.pcm + t.src_byte_off + 16 * kHop * 2 - 16, bytes_b, bar + s0);
+  } else if (!(t.flags & 1)) {
     const unsigned bytes = (unsigned)(((t.nf - 1) * kHop + kFrameLen) * 2) + lead;
     tma_load_1d(sRaw + s0 * kSlotBytes + 16 - lead, p.pcm + t.src_byte_off - lead, bytes, bar + s0);
   } else {
@@ -609,7 +652,10 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
         const int r = lane & 15;
         u64* exch = sExch + warp * kExchPerWarp + half * (16 * kExchStride);
         const int partner = (lane & 16) | ((16 - r) & 15);
-        const int fA = 4 * warp + 2 * half;  // frames fA, fA + 1 (even: 64-bit P stores)
+        // frames fA, fA + 1 (even: 64-bit P stores).  Full int16 tiles are staged as two regions and the
+        // upper half-warp takes its pair from the second one (frames 16..31): conflict-free row loads
+        const bool split = JS2T_SPLIT_STAGING && !f32 && nf == kTileFrames;
+        const int fA = split ? 2 * warp + 16 * half : 4 * warp + 2 * half;
         // past-the-end frame pairs redo the last valid pair (results land in unused columns of P)
         const int lA = min(fA, (nf - 1) & ~1);
         C2 v[16];
@@ -626,7 +672,9 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
           float sa = 0.f, sb = 0.f, mid = 0.f;
           const unsigned char* slot0 = sRaw + (kslot & 1u) * kSlotBytes;
           if (!f32) {
-            const unsigned* rw = reinterpret_cast<const unsigned*>(slot0 + 16) + 80 * lA + r;
+            const unsigned* rw = (split && half)
+                                     ? reinterpret_cast<const unsigned*>(slot0 + 16 + kSplitOff) + 80 * (lA - 16) + r
+                                     : reinterpret_cast<const unsigned*>(slot0 + 16) + 80 * lA + r;
             constexpr float kMagic = 8421376.0f;
 #pragma unroll
             for (int n = 0; n < 18; ++n) {
