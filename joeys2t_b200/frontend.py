@@ -106,9 +106,9 @@ def _as_1d_pcm(w: Array) -> np.ndarray:
 class PackedPCM:
     """Ragged batch packed into one pinned byte buffer, every utterance 16-byte aligned."""
 
-    def __init__(self, waveforms: Sequence[Array], host: Optional[torch.Tensor] = None):
+    def __init__(self, waveforms: Sequence[Array], host=None):
         """:param host: optional pinned uint8 tensor to pack into (reused staging buffer of a
-            streaming caller); must be large enough"""
+            streaming caller; must be large enough), or a callable ``nbytes -> tensor`` that provides one"""
         arrs = [_as_1d_pcm(w) for w in waveforms]
         self.n_samples = np.array([a.shape[0] for a in arrs], np.int64)
         self.is_f32 = np.array([a.dtype != np.int16 for a in arrs], np.uint8)
@@ -116,6 +116,8 @@ class PackedPCM:
         aligned = (sizes + 15) // 16 * 16
         self.byte_off = np.concatenate([[0], np.cumsum(aligned)[:-1]]).astype(np.int64)
         self.nbytes = int(aligned.sum())
+        if callable(host):
+            host = host(max(self.nbytes, 16))
         if host is not None:
             if host.dtype != torch.uint8 or host.numel() < self.nbytes:
                 raise ValueError(f"staging buffer too small: {host.numel()} < {self.nbytes} bytes")
@@ -298,13 +300,10 @@ def _staging(nbytes: int) -> torch.Tensor:
     memory per call cost more than the kernels for a single utterance."""
     buf = getattr(_tls, "staging", None)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes * 1.5), 1 << 20), dtype=torch.uint8, pin_memory=True)
+        buf = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, pin_memory=True)
         _tls.staging = buf
     return buf
 
-
-def _packed_nbytes(waveforms: Sequence[Array]) -> int:
-    return sum((int(np.shape(w)[-1]) * 4 + 15) // 16 * 16 for w in waveforms)  # upper bound (float32)
 
 def fbank_cmvn_specaug_ragged(
     waveforms: Sequence[Array],
@@ -330,7 +329,7 @@ def fbank_cmvn_specaug_ragged(
     :returns: (features on the GPU — ragged ``(sum T, 80)`` or padded ``(B, Tmax, 80)`` —, n_frames)
     """
     _require_cuda()
-    packed = PackedPCM(waveforms, host=_staging(_packed_nbytes(waveforms)))
+    packed = PackedPCM(waveforms, host=_staging)
     plan = Plan(packed.n_samples, packed.byte_off, packed.is_f32, max_frames=max_frames,
                 layout=layout, pad_value=pad_value)
     if global_stats is not None:
