@@ -7,11 +7,12 @@
 //   joeynmt/data_augmentation.py:38-73          SpecAugment    (host-drawn masks, apply kernel)
 //   joeynmt/helpers_for_audio.py:130-170        pad_features   (padded (B,Tmax,80) layout, pad 1.0)
 //
-// Work decomposition: one CTA (256 threads, 8 warps) per tile of 32 consecutive frames of one
-// utterance of the ragged batch.  Per tile:
-//   1. stage  the tile's PCM (int16 or fp32, 128-bit coalesced loads) into shared memory as the
-//             frame-independent pre-emphasised signal d[j] = x[j] - 0.97 x[j-1], plus 8-sample
-//             partial sums that give every frame's DC mean without re-reading the samples;
+// Work decomposition: persistent CTAs (256 threads, 8 warps, two per SM) take tiles of 32 consecutive
+// frames of one utterance of the ragged batch from a global counter; the tile's PCM arrives in a
+// shared-memory slot by bulk async copy (TMA 1-D) one iteration ahead.  Per tile:
+//   1. load   inside the FFT warps, straight from the PCM slot: lane r of a half-warp owns samples 2r,
+//             2r+1 of every 32-sample row, 18 row loads serve both frames of a pair (hop = 5 rows);
+//             int16 -> float, d[j] = x[j] - 0.97 x[j-1], running sums for the two DC means;
 //   2. fft    each half-warp transforms TWO frames at once with packed FP32x2 arithmetic (FADD2 /
 //             FMUL2 / FFMA2: one register pair = the same value of two frames): z[n] = y[2n] +
 //             i y[2n+1] (y = windowed frame, zero-padded to 512) as a 256-point complex FFT =
@@ -19,9 +20,11 @@
 //             registers; the real-input split (partner bin 256-k fetched with warp shuffles)
 //             yields the power spectrum directly;
 //   3. mel    lane = frame, warp = run of consecutive mel filters; the sparsity structure of the
-//             mel bank is compile-time (mel_structure.inc), the weights are __constant__ operands;
+//             mel bank is compile-time (mel_structure.inc), the weights are FFMA immediates;
 //   4. store  log-mel tile to HBM with coalesced stores (+ per-tile column sums / sums of squares
 //             for CMVN, or normalisation + masking right here when the statistics are known).
+// The finalize and apply kernels (utterance CMVN, SpecAugment fill, padding rows) follow, chained by
+// programmatic dependent launch; the apply kernel reads the rows back out of L2, newest tiles first.
 // FP32 throughout: the path is a small FP32 contraction, not a tensor-core workload.
 #include "js2t_internal.h"
 
