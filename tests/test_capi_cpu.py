@@ -84,3 +84,30 @@ def test_packed_pcm_alignment():
     assert np.array_equal(hv[:802].view(np.int16), waves[0])
     o = int(p.byte_off[2])
     assert np.array_equal(hv[o:o + 1998].view(np.int16), waves[2])
+
+
+def test_packed_pcm_into_caller_staging():
+    """PackedPCM packs into a caller-provided staging buffer (a tensor, or a callable that sizes one)
+    exactly as into its own, and refuses a buffer that is too small."""
+    import torch
+    from joeys2t_b200 import frontend
+    rng = np.random.default_rng(0)
+    waves = [rng.integers(-100, 100, 401).astype(np.int16), (rng.random(777) - 0.5).astype(np.float32),
+             rng.integers(-100, 100, (2, 1000)).astype(np.int16)]  # (C, N): channel 0 is taken (quirk Q1)
+    own = frontend.PackedPCM(waves)
+    asked = []
+
+    def provide(nbytes):
+        asked.append(nbytes)
+        return torch.full((nbytes + 64,), 0xAB, dtype=torch.uint8)
+
+    for host in (torch.zeros(own.nbytes + 100, dtype=torch.uint8), provide):
+        p = frontend.PackedPCM(waves, host=host)
+        assert p.nbytes == own.nbytes and np.array_equal(p.byte_off, own.byte_off)
+        assert np.array_equal(p.n_samples, [401, 777, 1000]) and p.is_f32.tolist() == [0, 1, 0]
+        for a, o in zip((waves[0], waves[1], waves[2][0]), p.byte_off):
+            got = p.host.numpy()[o:o + a.nbytes]
+            assert got.tobytes() == a.tobytes()
+    assert asked == [own.nbytes]
+    with pytest.raises(ValueError):
+        frontend.PackedPCM(waves, host=torch.zeros(own.nbytes - 1, dtype=torch.uint8))
