@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -316,18 +317,25 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
       t.out_row0 = d.out_row + f0;
       t.utt = u;
       t.frame0 = f0;
-      t.utt_tiles = (d.n_frames + kTileFrames - 1) / kTileFrames;
+      t.stats_slot = (int)tiles.size();
+      const int utt_tiles = (d.n_frames + kTileFrames - 1) / kTileFrames;
       const int nfv = d.n_frames - f0 < 0 ? 0 : (d.n_frames - f0 > kTileFrames ? kTileFrames : d.n_frames - f0);
       t.nf = (unsigned char)nfv;
       t.rows = (unsigned char)(span - f0 > kTileFrames ? kTileFrames : span - f0);
       t.flags = (unsigned char)(d.flags & 1);
       t.pad_ = 0;
-      if (t.utt_tiles > p->max_utt_tiles) p->max_utt_tiles = t.utt_tiles;
+      if (utt_tiles > p->max_utt_tiles) p->max_utt_tiles = utt_tiles;
       tiles.push_back(t);
     }
   }
   p->out_rows = row;
   p->n_tiles = (int)tiles.size();
+  // Processing order: the persistent kernel hands tiles out in array order, so the cheap ones — the
+  // partial last tile of every utterance, then pure padding — go to the end, where they shorten the
+  // tail in which CTAs run out of work (full tiles keep their utterance order).  Where a tile's rows
+  // and statistics land does not depend on this order (out_row0, stats_slot).
+  std::stable_sort(tiles.begin(), tiles.end(),
+                   [](const TileDesc& a, const TileDesc& b) { return a.nf > b.nf; });
 
   // one device allocation, carved up
   size_t off = 0;

@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
 
     if (nf == 0) {  // pure padding tile
       if (p.tile_stats != nullptr && tid < kStatsPerTile)
-        p.tile_stats[(long long)tile * kStatsPerTile + tid] = 0.f;
+        p.tile_stats[(long long)cur.stats_slot * kStatsPerTile + tid] = 0.f;
       for (int e = tid; e < rows * kMel; e += kThreads) out_tile[e] = p.pad_value;
     } else {
       // ---- phase 1: wait for this tile's PCM (bulk async copy issued one tile ago) ---------------------
@@ -943,7 +943,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
               float acc = 0.f;
 #pragma unroll
               for (int w = 0; w < kWarps; ++w) acc += sStat[w * kStatsPerTile + tid];
-              p.tile_stats[(long long)tile * kStatsPerTile + tid] = acc;
+              p.tile_stats[(long long)cur.stats_slot * kStatsPerTile + tid] = acc;
             }
           }
         } else if (kMode == kModeNormKnown) {  // (x - mean) * istd and SpecAugment fill at store
@@ -1034,7 +1034,7 @@ __global__ void __launch_bounds__(kThreads) feature_tile_kernel(const FbankLaunc
       const float x = in_tile[f * kMel + m];
       acc += sq ? x * x : x;
     }
-    p.tile_stats[(long long)blockIdx.x * kStatsPerTile + tid] = acc;
+    p.tile_stats[(long long)td.stats_slot * kStatsPerTile + tid] = acc;
   }
 }
 

@@ -33,7 +33,8 @@ struct TileDesc {
   long long out_row0;      // first output row of the tile
   int utt;
   int frame0;              // first frame of the tile inside the utterance
-  int utt_tiles;           // number of non-empty tiles of this utterance
+  int stats_slot;          // row of the per-tile statistics array: the tile's index in utterance order
+                           // (tiles are PROCESSED full ones first, see js2t_plan_create)
   unsigned char nf;        // valid frames in the tile (0 => pure padding tile of the padded layout)
   unsigned char rows;      // output rows the tile owns (>= nf; the rest is padding)
   unsigned char flags;     // bit0: PCM is fp32
