@@ -13,8 +13,11 @@
  *     last failure on the calling thread; no exceptions cross the boundary;
  *   - pointers named *_dev are CUDA device pointers owned by the caller, everything else is host
  *     memory; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
- *   - all GPU work is enqueued asynchronously on `stream`; nothing here synchronises the device
- *     except js2t_plan_create / js2t_ctx_create / *_destroy (allocation);
+ *   - all GPU work is enqueued asynchronously on `stream`; nothing synchronises the whole device except
+ *     js2t_ctx_set_tables (once).  js2t_plan_create uploads its descriptors asynchronously on a stream of
+ *     the context and orders every stream the plan is later used on behind that upload; js2t_plan_destroy
+ *     waits only for the streams the plan was used on;
+ *   - every call runs on the context's device and restores the caller's current device before returning;
  *   - there is no CPU fallback: without a usable CUDA device every call fails with JS2T_ERR_CUDA.
  *
  * Geometry is the reference's fixed one: 16 kHz, 25 ms / 10 ms frames (400 / 160 samples),
@@ -137,8 +140,7 @@ int js2t_plan_enable_profiling(js2t_plan* plan, int n_slots);
 int js2t_plan_kernel_times_ms(js2t_plan* plan, float* ms_out, int n, int* n_written);
 
 /* Tuning switches: "max_ctas" caps the persistent grid, "debug_times" records per-tile time stamps,
- * "debug_skip" skips kernel phases in -DJS2T_DBG=1 builds.  "fused_cmvn" / "force_unfused" are
- * accepted and ignored (the in-kernel CMVN variants of round 1 were slower and were removed). */
+ * "debug_skip" skips kernel phases in -DJS2T_DBG=1 builds.  Unknown names are an error. */
 int js2t_plan_set_option(js2t_plan* plan, const char* name, int value);
 /* With option "debug_times" = 1: per-tile %globaltimer stamps [n_tiles][4] (tile start, stored,
  * published, normalised-older-tile) of the last execute, copied to host memory (synchronous). */
@@ -159,6 +161,15 @@ int js2t_plan_copy_utt_stats(const js2t_plan* plan, double* dst_dev, void* strea
  * normalize applies them (and the SpecAugment fill) in place to raw log-mel in out_dev. */
 int js2t_global_stats_accumulate(js2t_plan* plan, double* accum_dev, void* stream);
 int js2t_global_stats_allreduce(void* nccl_comm, double* accum_dev, void* stream);
+/* The communicator for it.  The reference reduces with torch.distributed (joeynmt/helpers_for_ddp.py:
+ * 157-174 ddp_reduce: dist.all_reduce(SUM)) over ranks that shard the data as indices[rank::world]
+ * (helpers_for_ddp.py:319); a C host has no process group, so the ABI carries the three NCCL calls
+ * it needs: rank 0 draws a 128-byte unique id and ships it to the other ranks by whatever channel the
+ * host has (torch.distributed broadcast, MPI, a file), then every rank creates its communicator
+ * (collective call).  libnccl is bound at run time from the host process. */
+int js2t_nccl_unique_id(void* id128_out);
+int js2t_nccl_comm_create(const void* id128, int world_size, int rank, int device, void** comm_out);
+int js2t_nccl_comm_destroy(void* nccl_comm);
 int js2t_global_stats_finalize(js2t_plan* plan, const double* accum_dev, void* stream);
 int js2t_normalize_execute(js2t_plan* plan, float* out_dev, void* stream);
 

@@ -33,7 +33,8 @@ EXPORTED_SYMBOLS = [
     "js2t_plan_set_cmvn", "js2t_plan_set_global_stats", "js2t_plan_set_masks", "js2t_fbank_execute",
     "js2t_features_execute", "js2t_plan_enable_profiling", "js2t_plan_kernel_times_ms",
     "js2t_plan_set_option", "js2t_plan_debug_times", "js2t_plan_utt_stats", "js2t_plan_copy_utt_stats", "js2t_global_stats_accumulate",
-    "js2t_global_stats_allreduce", "js2t_global_stats_finalize", "js2t_normalize_execute",
+    "js2t_global_stats_allreduce", "js2t_nccl_unique_id", "js2t_nccl_comm_create", "js2t_nccl_comm_destroy",
+    "js2t_global_stats_finalize", "js2t_normalize_execute",
     "js2t_reformat_48k_to_16k",
 ]
 
@@ -114,6 +115,9 @@ def _declare(lib):
     lib.js2t_plan_copy_utt_stats.argtypes = [vp, vp, vp]
     lib.js2t_global_stats_accumulate.argtypes = [vp, vp, vp]
     lib.js2t_global_stats_allreduce.argtypes = [vp, vp, vp]
+    lib.js2t_nccl_unique_id.argtypes = [vp]
+    lib.js2t_nccl_comm_create.argtypes = [vp, i32, i32, i32, P(vp)]
+    lib.js2t_nccl_comm_destroy.argtypes = [vp]
     lib.js2t_global_stats_finalize.argtypes = [vp, vp, vp]
     lib.js2t_normalize_execute.argtypes = [vp, vp, vp]
     lib.js2t_reformat_48k_to_16k.argtypes = [vp, vp, i32, i64, vp, vp, vp]

@@ -40,12 +40,31 @@ int fail(int code, const char* fmt, ...) {
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Entry points run on the context's device and leave the caller's current device as they found it
+// (a caller driving several GPUs from one thread must not have its device changed under it).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err;
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+    else if (err == cudaSuccess) prev = -1;  // nothing to restore
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 }  // namespace
 
 struct js2t_ctx {
   int device = 0;
   float* d_tables = nullptr;  // window_half[400] | tw256[256 x float2] | tw512[136 x float2]
   bool tables_set = false;
+  // plan descriptors are uploaded on this (non-blocking) stream; every plan records an event behind its
+  // upload and every execute stream waits for it, so the upload is formally ordered before the kernels
+  // on whatever stream the caller launches them and plan creation never synchronises the device
+  cudaStream_t upload_stream = nullptr;
   // Device-buffer pool for plan workspaces: the per-item / per-batch callers of the reference API create
   // and destroy one plan per call, and cudaMalloc + cudaFree were a third of such a call.
   std::mutex pool_mu;
@@ -130,7 +149,31 @@ struct js2t_plan {
   // optional instrumentation: CUDA events around the fbank kernel of each execute (ring of slots)
   std::vector<cudaEvent_t> prof_ev;  // 2 per slot
   long long prof_calls = 0;
+  cudaEvent_t ready_ev = nullptr;  // recorded behind the descriptor upload (ctx->upload_stream)
+  std::vector<cudaStream_t> streams;  // streams the plan has enqueued work on (normally one)
 };
+
+namespace {
+
+// Everything the plan enqueues on `stream` comes after its descriptors have landed: the first time a
+// stream is used it waits for ready_ev; afterwards stream order guarantees it.  (Nothing is inserted
+// between the kernels of consecutive steps, which would undo their programmatic dependent launch.)
+cudaError_t plan_begin(js2t_plan* plan, cudaStream_t stream) {
+  for (cudaStream_t s : plan->streams)
+    if (s == stream) return cudaSuccess;
+  plan->streams.push_back(stream);
+  return cudaStreamWaitEvent(stream, plan->ready_ev, 0);
+}
+// Wait (host side) until nothing in flight reads the plan's workspace any more: the streams the plan was
+// used on, not the whole device — other streams keep running.  A stream the caller has destroyed in the
+// meantime had to be drained for that, so its error is ignored.
+void plan_quiesce(js2t_plan* plan) {
+  if (plan->ready_ev) cudaEventSynchronize(plan->ready_ev);
+  for (cudaStream_t s : plan->streams)
+    if (cudaStreamSynchronize(s) != cudaSuccess) cudaGetLastError();
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -153,15 +196,18 @@ int js2t_ctx_create(int device, js2t_ctx** out) {
   if (prop.major < 10)
     return fail(JS2T_ERR_CUDA, "js2t_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
                 device, prop.major, prop.minor);
-  JS2T_CUDA(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  JS2T_CUDA(guard.err);
   js2t_ctx* c = new (std::nothrow) js2t_ctx();
   if (c == nullptr) return fail(JS2T_ERR_INVALID, "out of host memory");
   c->device = device;
   const size_t bytes = (400 + 2 * 256 + 2 * 136) * sizeof(float);
   cudaError_t e = cudaMalloc(&c->d_tables, bytes);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
+    if (c->d_tables) cudaFree(c->d_tables);
     delete c;
-    return fail(JS2T_ERR_CUDA, "cudaMalloc(tables) failed: %s", cudaGetErrorString(e));
+    return fail(JS2T_ERR_CUDA, "context allocation failed: %s", cudaGetErrorString(e));
   }
   *out = c;
   return JS2T_OK;
@@ -169,7 +215,11 @@ int js2t_ctx_create(int device, js2t_ctx** out) {
 
 int js2t_ctx_destroy(js2t_ctx* ctx) {
   if (ctx == nullptr) return JS2T_OK;
-  cudaSetDevice(ctx->device);
+  DeviceGuard guard(ctx->device);
+  if (ctx->upload_stream) {
+    cudaStreamSynchronize(ctx->upload_stream);
+    cudaStreamDestroy(ctx->upload_stream);
+  }
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   for (auto& b : ctx->pool) cudaFree(b.second);
   delete ctx;
@@ -222,10 +272,12 @@ int js2t_ctx_set_tables(js2t_ctx* ctx, const float* window400, const float* mel8
     tw512[2 * k] = (float)cos(a);
     tw512[2 * k + 1] = (float)sin(a);
   }
-  JS2T_CUDA(cudaSetDevice(ctx->device));
+  DeviceGuard guard(ctx->device);
+  JS2T_CUDA(guard.err);
+  // once per context; synchronous on purpose: the tables are complete before any stream can use them
   JS2T_CUDA(cudaMemcpy(ctx->d_tables, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
   JS2T_CUDA(upload_mel_weights(wu, wd, 0));
-  JS2T_CUDA(cudaStreamSynchronize(0));
+  JS2T_CUDA(cudaDeviceSynchronize());
   ctx->tables_set = true;
   return JS2T_OK;
 }
@@ -349,8 +401,9 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
   const size_t o_g = carve(sizeof(float) * 2 * kMel);
   const size_t o_ustats = carve(sizeof(double) * kStatsPerTile * n_utts);
   const size_t o_sched = carve(sizeof(int) * 2);
-  cudaSetDevice(ctx->device);
-  cudaError_t e = pool_alloc(ctx, off, &p->d_ws, &p->ws_cap);
+  DeviceGuard guard(ctx->device);
+  cudaError_t e = guard.err;
+  if (e == cudaSuccess) e = pool_alloc(ctx, off, &p->d_ws, &p->ws_cap);
   if (e != cudaSuccess) {
     delete p;
     return fail(JS2T_ERR_CUDA, "cudaMalloc(%zu bytes of plan workspace) failed: %s", off, cudaGetErrorString(e));
@@ -366,11 +419,20 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
   p->d_gistd = p->d_gmean + kMel;
   p->d_utt_stats = reinterpret_cast<double*>(base + o_ustats);
   p->d_sched = reinterpret_cast<int*>(base + o_sched);
-  e = cudaMemset(p->d_sched, 0, sizeof(int) * 2);
-  if (e == cudaSuccess) e = cudaMemcpy(p->d_utts, p->h_utts.data(), sizeof(UttDesc) * n_utts, cudaMemcpyHostToDevice);
+  // Asynchronous upload on the context's own stream.  The sources are pageable: cudaMemcpyAsync returns
+  // once they have been staged (so `tiles` may go out of scope), and the DMA itself is ordered on
+  // upload_stream in front of ready_ev, which every execute stream waits for (plan_begin).
+  e = cudaEventCreateWithFlags(&p->ready_ev, cudaEventDisableTiming);
+  cudaStream_t us = ctx->upload_stream;
+  if (e == cudaSuccess) e = cudaMemsetAsync(p->d_sched, 0, sizeof(int) * 2, us);
   if (e == cudaSuccess)
-    e = cudaMemcpy(p->d_tiles, tiles.data(), sizeof(TileDesc) * tiles.size(), cudaMemcpyHostToDevice);
+    e = cudaMemcpyAsync(p->d_utts, p->h_utts.data(), sizeof(UttDesc) * n_utts, cudaMemcpyHostToDevice, us);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(p->d_tiles, tiles.data(), sizeof(TileDesc) * tiles.size(), cudaMemcpyHostToDevice, us);
+  if (e == cudaSuccess) e = cudaEventRecord(p->ready_ev, us);
   if (e != cudaSuccess) {
+    cudaStreamSynchronize(us);
+    if (p->ready_ev) cudaEventDestroy(p->ready_ev);
     pool_free(ctx, p->d_ws, p->ws_cap);
     delete p;
     return fail(JS2T_ERR_CUDA, "plan descriptor upload failed: %s", cudaGetErrorString(e));
@@ -395,10 +457,12 @@ int js2t_plan_create_features(js2t_ctx* ctx, int n_utts, const int32_t* n_frames
 
 int js2t_plan_destroy(js2t_plan* plan) {
   if (plan == nullptr) return JS2T_OK;
-  cudaSetDevice(plan->ctx->device);
+  DeviceGuard guard(plan->ctx->device);
   for (cudaEvent_t e : plan->prof_ev) cudaEventDestroy(e);
-  // like the cudaFree it replaces, destroying a plan waits for whatever still uses its workspace
-  cudaDeviceSynchronize();
+  // like the cudaFree it replaces, destroying a plan waits for whatever still uses its workspace —
+  // but only for that (an event behind the plan's latest launch), not for the whole device
+  plan_quiesce(plan);
+  if (plan->ready_ev) cudaEventDestroy(plan->ready_ev);
   if (plan->d_masks) pool_free(plan->ctx, plan->d_masks, plan->masks_cap);
   if (plan->d_dbg) cudaFree(plan->d_dbg);
   if (plan->d_ws) pool_free(plan->ctx, plan->d_ws, plan->ws_cap);
@@ -439,9 +503,11 @@ int js2t_plan_set_global_stats(js2t_plan* plan, const double* mean80, const doub
     h[b] = (float)mean80[b];
     h[kMel + b] = (float)istd80[b];
   }
-  JS2T_CUDA(cudaSetDevice(plan->ctx->device));
+  DeviceGuard guard(plan->ctx->device);
+  JS2T_CUDA(guard.err);
+  // pageable source: the call returns once h has been staged, the DMA is ordered on `stream`
+  JS2T_CUDA(plan_begin(plan, (cudaStream_t)stream));
   JS2T_CUDA(cudaMemcpyAsync(plan->d_gmean, h, sizeof(h), cudaMemcpyHostToDevice, (cudaStream_t)stream));
-  JS2T_CUDA(cudaStreamSynchronize((cudaStream_t)stream));  // h is on the stack
   plan->global_stats_set = true;
   return JS2T_OK;
 }
@@ -458,10 +524,11 @@ int js2t_plan_set_masks(js2t_plan* plan, int n_fmask, int n_tmask, const int32_t
   if (value_mode != JS2T_MASK_VALUE_MEAN && value_mode != JS2T_MASK_VALUE_CONST)
     return fail(JS2T_ERR_INVALID, "unknown mask value mode %d", value_mode);
   const size_t bytes = sizeof(int32_t) * 2 * (size_t)(n_fmask + n_tmask) * plan->n_utts;
-  JS2T_CUDA(cudaSetDevice(plan->ctx->device));
+  DeviceGuard guard(plan->ctx->device);
+  JS2T_CUDA(guard.err);
   if (bytes > plan->masks_cap) {
     if (plan->d_masks) {
-      JS2T_CUDA(cudaDeviceSynchronize());  // an earlier execute may still read the old table
+      plan_quiesce(plan);  // an earlier execute may still read the old table
       pool_free(plan->ctx, plan->d_masks, plan->masks_cap);
     }
     plan->d_masks = nullptr;
@@ -472,6 +539,8 @@ int js2t_plan_set_masks(js2t_plan* plan, int n_fmask, int n_tmask, const int32_t
     plan->d_masks = static_cast<int*>(m);
     plan->masks_cap = cap;
   }
+  // pageable source: staged when the call returns (the caller may reuse `table`), DMA ordered on `stream`
+  JS2T_CUDA(plan_begin(plan, (cudaStream_t)stream));
   JS2T_CUDA(cudaMemcpyAsync(plan->d_masks, table, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
   plan->n_fmask = n_fmask;
   plan->n_tmask = n_tmask;
@@ -544,11 +613,13 @@ static int run_pipeline(js2t_plan* plan, const void* in_dev, float* out_dev, cud
                                          : "js2t_features_execute needs a plan made by js2t_plan_create_features");
   if (from_pcm && !plan->ctx->tables_set)
     return fail(JS2T_ERR_STATE, "js2t_ctx_set_tables has not been called");
-  JS2T_CUDA(cudaSetDevice(plan->ctx->device));
+  DeviceGuard guard(plan->ctx->device);
+  JS2T_CUDA(guard.err);
   const int mode = plan->cmvn_mode;
   const bool masks = plan->has_masks;
   if (mode == JS2T_CMVN_GLOBAL && !plan->global_stats_set)
     return fail(JS2T_ERR_STATE, "global CMVN requested but no statistics were set");
+  JS2T_CUDA(plan_begin(plan, stream));
 
   FbankLaunch f;
   memset(&f, 0, sizeof(f));
@@ -611,9 +682,10 @@ static int run_pipeline(js2t_plan* plan, const void* in_dev, float* out_dev, cud
   FinalizeLaunch z = make_finalize(plan, out_dev, shared);
   JS2T_CUDA(launch_finalize(z, stream));
   plan->stats_valid = true;
-  if (mode == JS2T_CMVN_STATS_ONLY) return JS2T_OK;
-  ApplyLaunch a = make_apply(plan, out_dev, shared);
-  JS2T_CUDA(launch_apply(a, stream));
+  if (mode != JS2T_CMVN_STATS_ONLY) {
+    ApplyLaunch a = make_apply(plan, out_dev, shared);
+    JS2T_CUDA(launch_apply(a, stream));
+  }
   return JS2T_OK;
 }
 
@@ -627,7 +699,8 @@ int js2t_features_execute(js2t_plan* plan, const float* feats_dev, float* out_de
 
 int js2t_plan_enable_profiling(js2t_plan* plan, int n_slots) {
   if (plan == nullptr || n_slots < 0) return fail(JS2T_ERR_INVALID, "bad argument");
-  JS2T_CUDA(cudaSetDevice(plan->ctx->device));
+  DeviceGuard guard(plan->ctx->device);
+  JS2T_CUDA(guard.err);
   for (cudaEvent_t e : plan->prof_ev) cudaEventDestroy(e);
   plan->prof_ev.clear();
   plan->prof_calls = 0;
@@ -656,8 +729,6 @@ int js2t_plan_kernel_times_ms(js2t_plan* plan, float* ms_out, int n, int* n_writ
 
 int js2t_plan_set_option(js2t_plan* plan, const char* name, int value) {
   if (plan == nullptr || name == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
-  if (strcmp(name, "fused_cmvn") == 0 || strcmp(name, "force_unfused") == 0)
-    return JS2T_OK;  // accepted for compatibility: the in-kernel variant was removed
   if (strcmp(name, "max_ctas") == 0) {
     plan->grid_limit = value;
     return JS2T_OK;
@@ -667,7 +738,8 @@ int js2t_plan_set_option(js2t_plan* plan, const char* name, int value) {
     return JS2T_OK;
   }
   if (strcmp(name, "debug_times") == 0) {
-    JS2T_CUDA(cudaSetDevice(plan->ctx->device));
+    DeviceGuard guard(plan->ctx->device);
+  JS2T_CUDA(guard.err);
     if (value != 0 && plan->d_dbg == nullptr) {
       // [n_tiles][4] per-tile stamps + [n_tiles][8 warps][8] per-warp stamps (JS2T_DBG builds)
       JS2T_CUDA(cudaMalloc(&plan->d_dbg, sizeof(unsigned long long) * 68 * plan->n_tiles));
@@ -685,7 +757,8 @@ int js2t_plan_debug_times(const js2t_plan* plan, unsigned long long* host_out, i
   if (plan == nullptr || host_out == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
   if (plan->d_dbg == nullptr) return fail(JS2T_ERR_STATE, "option debug_times is off");
   if (n_values > 68ll * plan->n_tiles) n_values = 68ll * plan->n_tiles;
-  JS2T_CUDA(cudaSetDevice(plan->ctx->device));
+  DeviceGuard guard(plan->ctx->device);
+  JS2T_CUDA(guard.err);
   JS2T_CUDA(cudaMemcpy(host_out, plan->d_dbg, sizeof(unsigned long long) * n_values, cudaMemcpyDeviceToHost));
   return JS2T_OK;
 }
@@ -693,7 +766,9 @@ int js2t_plan_debug_times(const js2t_plan* plan, unsigned long long* host_out, i
 int js2t_plan_copy_utt_stats(const js2t_plan* plan, double* dst_dev, void* stream) {
   if (plan == nullptr || dst_dev == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
   if (!plan->stats_valid) return fail(JS2T_ERR_STATE, "no statistics: run js2t_fbank_execute in a statistics mode first");
-  JS2T_CUDA(cudaSetDevice(plan->ctx->device));
+  DeviceGuard guard(plan->ctx->device);
+  JS2T_CUDA(guard.err);
+  JS2T_CUDA(plan_begin(const_cast<js2t_plan*>(plan), (cudaStream_t)stream));
   JS2T_CUDA(cudaMemcpyAsync(dst_dev, plan->d_utt_stats, sizeof(double) * kStatsPerTile * plan->n_utts,
                             cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return JS2T_OK;
@@ -710,34 +785,109 @@ int js2t_plan_utt_stats(const js2t_plan* plan, const double** stats_dev) {
 int js2t_global_stats_accumulate(js2t_plan* plan, double* accum_dev, void* stream) {
   if (plan == nullptr || accum_dev == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
   if (!plan->stats_valid) return fail(JS2T_ERR_STATE, "no statistics to accumulate");
-  JS2T_CUDA(cudaSetDevice(plan->ctx->device));
+  DeviceGuard guard(plan->ctx->device);
+  JS2T_CUDA(guard.err);
+  JS2T_CUDA(plan_begin(plan, (cudaStream_t)stream));
   JS2T_CUDA(launch_global_accumulate(plan->d_utt_stats, plan->d_utts, plan->n_utts, accum_dev,
                                      (cudaStream_t)stream));
   return JS2T_OK;
 }
 
-int js2t_global_stats_allreduce(void* nccl_comm, double* accum_dev, void* stream) {
-  if (nccl_comm == nullptr || accum_dev == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
-  // ncclResult_t ncclAllReduce(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t)
-  typedef int (*allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
-  static allreduce_fn fn = nullptr;
-  if (fn == nullptr) {
+// ---- NCCL, bound at run time --------------------------------------------------------------------
+// libnccl is not linked: it is looked up in the process when the first communicator call is made, so the
+// library of the host application (torch bundles its own libnccl.so.2) is the one that is used, and
+// single-GPU users need no NCCL at all.
+namespace {
+
+struct NcclUniqueId {
+  char internal[128];  // NCCL_UNIQUE_ID_BYTES
+};
+struct NcclApi {
+  int (*get_unique_id)(NcclUniqueId*) = nullptr;
+  int (*comm_init_rank)(void**, int, NcclUniqueId, int) = nullptr;
+  int (*comm_destroy)(void*) = nullptr;
+  int (*all_reduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*get_error_string)(int) = nullptr;
+  bool ok = false;
+};
+
+const NcclApi* nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
     void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (h == nullptr) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-    if (h == nullptr) return fail(JS2T_ERR_NCCL, "cannot load libnccl: %s", dlerror());
-    fn = reinterpret_cast<allreduce_fn>(dlsym(h, "ncclAllReduce"));
-    if (fn == nullptr) return fail(JS2T_ERR_NCCL, "ncclAllReduce not found in libnccl");
-  }
+    if (h == nullptr) return;
+    api.get_unique_id = reinterpret_cast<decltype(api.get_unique_id)>(dlsym(h, "ncclGetUniqueId"));
+    api.comm_init_rank = reinterpret_cast<decltype(api.comm_init_rank)>(dlsym(h, "ncclCommInitRank"));
+    api.comm_destroy = reinterpret_cast<decltype(api.comm_destroy)>(dlsym(h, "ncclCommDestroy"));
+    api.all_reduce = reinterpret_cast<decltype(api.all_reduce)>(dlsym(h, "ncclAllReduce"));
+    api.get_error_string = reinterpret_cast<decltype(api.get_error_string)>(dlsym(h, "ncclGetErrorString"));
+    api.ok = api.get_unique_id && api.comm_init_rank && api.comm_destroy && api.all_reduce;
+  });
+  return api.ok ? &api : nullptr;
+}
+
+int nccl_fail(const NcclApi* api, const char* what, int rc) {
+  return fail(JS2T_ERR_NCCL, "%s failed: %s (code %d)", what,
+              api->get_error_string ? api->get_error_string(rc) : "?", rc);
+}
+
+}  // namespace
+
+int js2t_nccl_unique_id(void* id128_out) {
+  if (id128_out == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
+  const NcclApi* api = nccl_api();
+  if (api == nullptr) return fail(JS2T_ERR_NCCL, "cannot load libnccl: %s", dlerror());
+  NcclUniqueId id;
+  const int rc = api->get_unique_id(&id);
+  if (rc != 0) return nccl_fail(api, "ncclGetUniqueId", rc);
+  memcpy(id128_out, &id, sizeof(id));
+  return JS2T_OK;
+}
+
+int js2t_nccl_comm_create(const void* id128, int world_size, int rank, int device, void** comm_out) {
+  if (id128 == nullptr || comm_out == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
+  if (world_size < 1 || rank < 0 || rank >= world_size)
+    return fail(JS2T_ERR_INVALID, "rank %d of %d", rank, world_size);
+  const NcclApi* api = nccl_api();
+  if (api == nullptr) return fail(JS2T_ERR_NCCL, "cannot load libnccl: %s", dlerror());
+  DeviceGuard guard(device);
+  JS2T_CUDA(guard.err);
+  NcclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  void* comm = nullptr;
+  const int rc = api->comm_init_rank(&comm, world_size, id, rank);  // collective over all ranks
+  if (rc != 0) return nccl_fail(api, "ncclCommInitRank", rc);
+  *comm_out = comm;
+  return JS2T_OK;
+}
+
+int js2t_nccl_comm_destroy(void* nccl_comm) {
+  if (nccl_comm == nullptr) return JS2T_OK;
+  const NcclApi* api = nccl_api();
+  if (api == nullptr) return fail(JS2T_ERR_NCCL, "cannot load libnccl");
+  const int rc = api->comm_destroy(nccl_comm);
+  if (rc != 0) return nccl_fail(api, "ncclCommDestroy", rc);
+  return JS2T_OK;
+}
+
+int js2t_global_stats_allreduce(void* nccl_comm, double* accum_dev, void* stream) {
+  if (nccl_comm == nullptr || accum_dev == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
+  const NcclApi* api = nccl_api();
+  if (api == nullptr) return fail(JS2T_ERR_NCCL, "cannot load libnccl: %s", dlerror());
   const int kNcclFloat64 = 8, kNcclSum = 0;
-  const int rc = fn(accum_dev, accum_dev, (size_t)(kStatsPerTile + 1), kNcclFloat64, kNcclSum, nccl_comm,
-                    (cudaStream_t)stream);
-  if (rc != 0) return fail(JS2T_ERR_NCCL, "ncclAllReduce failed with code %d", rc);
+  const int rc = api->all_reduce(accum_dev, accum_dev, (size_t)(kStatsPerTile + 1), kNcclFloat64, kNcclSum,
+                                 nccl_comm, (cudaStream_t)stream);
+  if (rc != 0) return nccl_fail(api, "ncclAllReduce", rc);
   return JS2T_OK;
 }
 
 int js2t_global_stats_finalize(js2t_plan* plan, const double* accum_dev, void* stream) {
   if (plan == nullptr || accum_dev == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
-  JS2T_CUDA(cudaSetDevice(plan->ctx->device));
+  DeviceGuard guard(plan->ctx->device);
+  JS2T_CUDA(guard.err);
+  JS2T_CUDA(plan_begin(plan, (cudaStream_t)stream));
   JS2T_CUDA(launch_global_finalize(accum_dev, plan->norm_means, plan->norm_vars, plan->d_gmean, plan->d_gistd,
                                    (cudaStream_t)stream));
   plan->global_stats_set = true;
@@ -750,7 +900,9 @@ int js2t_normalize_execute(js2t_plan* plan, float* out_dev, void* stream_) {
   if (!plan->stats_valid)
     return fail(JS2T_ERR_STATE, "js2t_normalize_execute follows a STATS_ONLY js2t_fbank_execute on the same plan");
   cudaStream_t stream = (cudaStream_t)stream_;
-  JS2T_CUDA(cudaSetDevice(plan->ctx->device));
+  DeviceGuard guard(plan->ctx->device);
+  JS2T_CUDA(guard.err);
+  JS2T_CUDA(plan_begin(plan, stream));
   const int saved = plan->cmvn_mode;
   plan->cmvn_mode = JS2T_CMVN_GLOBAL;
   // per-utterance fill value under the global normalisation (re-reads the per-tile statistics of the
@@ -776,7 +928,8 @@ int js2t_reformat_48k_to_16k(js2t_ctx* ctx, const void* src_dev, int is_f32, int
   if (src_dev == nullptr || dst_dev == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
   if ((reinterpret_cast<uintptr_t>(src_dev) & 15) != 0 || (reinterpret_cast<uintptr_t>(dst_dev) & 15) != 0)
     return fail(JS2T_ERR_INVALID, "src_dev and dst_dev must be 16-byte aligned");
-  JS2T_CUDA(cudaSetDevice(ctx->device));
+  DeviceGuard guard(ctx->device);
+  JS2T_CUDA(guard.err);
   JS2T_CUDA(launch_reformat_48k_to_16k(src_dev, is_f32, (long long)n_samples, dst_dev,
                                        static_cast<int*>(workspace_dev), (cudaStream_t)stream_));
   return JS2T_OK;

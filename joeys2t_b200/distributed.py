@@ -46,10 +46,65 @@ def new_accumulator(device=None) -> torch.Tensor:
     return torch.zeros(ACCUM_LEN, dtype=torch.float64, device=device)
 
 
-def allreduce_global_stats(accum: torch.Tensor, group=None) -> torch.Tensor:
+class NcclCommunicator:
+    """``ncclComm_t`` owned by the C ABI (``js2t_nccl_comm_create``), for the path's one collective.
+
+    The 128-byte NCCL unique id is drawn by rank 0 and broadcast over the existing
+    ``torch.distributed`` process group (the only thing torch is used for here); the communicator
+    itself and the all-reduce are the library's own ``ncclCommInitRank`` / ``ncclAllReduce`` calls.
+    """
+
+    def __init__(self, device: int, group=None):
+        import ctypes
+        from joeys2t_b200 import _lib
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("NcclCommunicator needs an initialised torch.distributed process group")
+        self._lib = _lib.load()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = int(device)
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (ctypes.c_ubyte * 128)()
+            _lib.check(self._lib.js2t_nccl_unique_id(buf))
+            uid = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone()
+        on_gpu = dist.get_backend(group) == "nccl"
+        t = uid.to(f"cuda:{self.device}") if on_gpu else uid
+        dist.broadcast(t, src=0, group=group)
+        raw = bytes(t.cpu().numpy().tobytes())
+        self._h = ctypes.c_void_p()
+        _lib.check(self._lib.js2t_nccl_comm_create(raw, self.world, self.rank, self.device,
+                                                   ctypes.byref(self._h)))
+
+    def allreduce_global_stats(self, accum: torch.Tensor) -> torch.Tensor:
+        """In-place SUM all-reduce of the (161,) float64 accumulator on the current stream."""
+        from joeys2t_b200 import _lib
+        assert accum.is_cuda and accum.dtype == torch.float64 and accum.numel() == ACCUM_LEN
+        stream = torch.cuda.current_stream(accum.device).cuda_stream
+        _lib.check(self._lib.js2t_global_stats_allreduce(self._h, accum.data_ptr(), stream))
+        return accum
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.js2t_nccl_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass
+
+
+def allreduce_global_stats(accum: torch.Tensor, group=None,
+                           comm: Optional["NcclCommunicator"] = None) -> torch.Tensor:
     """The path's single collective: in-place SUM all-reduce of the 161 float64 statistics,
-    enqueued on the current stream (NCCL) — no host synchronisation."""
+    enqueued on the current stream — no host synchronisation.  With ``comm`` it goes through the C ABI
+    (``js2t_global_stats_allreduce`` -> ``ncclAllReduce``); without, through ``torch.distributed``
+    (the route of the reference's own ``ddp_reduce``, helpers_for_ddp.py:157-174; ``gloo`` in the CPU
+    tests)."""
     assert accum.dtype == torch.float64 and accum.numel() == ACCUM_LEN
+    if comm is not None:
+        return comm.allreduce_global_stats(accum)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(accum, op=dist.ReduceOp.SUM, group=group)
     return accum

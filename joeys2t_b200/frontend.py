@@ -20,6 +20,7 @@ NUM_MEL = tables.NUM_MEL_BINS
 Array = Union[np.ndarray, torch.Tensor]
 
 _contexts = {}
+_contexts_lock = threading.Lock()
 
 
 def _require_cuda():
@@ -28,8 +29,10 @@ def _require_cuda():
             "joeys2t_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
 
 
-def _stream_ptr(stream: Optional[torch.cuda.Stream] = None) -> int:
-    return (stream or torch.cuda.current_stream()).cuda_stream
+def _stream_ptr(stream: Optional[torch.cuda.Stream] = None, device: Optional[int] = None) -> int:
+    """Raw ``cudaStream_t`` of ``stream``, or of torch's current stream ON ``device`` (a stream handle of
+    another device is an invalid resource handle for the launches of a plan on ``device``)."""
+    return (stream or torch.cuda.current_stream(device)).cuda_stream
 
 
 class Context:
@@ -61,9 +64,10 @@ def get_context(device: Optional[int] = None) -> Context:
     _require_cuda()
     if device is None:
         device = torch.cuda.current_device()
-    if device not in _contexts:
-        _contexts[device] = Context(device)
-    return _contexts[device]
+    with _contexts_lock:  # per-thread staging implies threaded callers
+        if device not in _contexts:
+            _contexts[device] = Context(device)
+        return _contexts[device]
 
 
 def bind_host_thread_to_gpu(device: Optional[int] = None) -> bool:
@@ -179,6 +183,10 @@ class Plan:
         self.pad_tmax = self.out_rows // self.n_utts if layout == "padded" else 0
         self._keepalive = None
 
+    def _stream(self) -> int:
+        """torch's current stream on the PLAN's device (not on whatever device is current)."""
+        return _stream_ptr(device=self.ctx.device)
+
     # ---- configuration ----------------------------------------------------------------------
     def set_cmvn(self, mode: str = "utterance", norm_means: bool = True, norm_vars: bool = True,
                  before: bool = True) -> "Plan":
@@ -193,22 +201,22 @@ class Plan:
         istd = np.ascontiguousarray(istd, np.float64)
         assert mean.shape == (NUM_MEL,) and istd.shape == (NUM_MEL,)
         _lib.check(self._lib.js2t_plan_set_global_stats(self._h, mean.ctypes.data, istd.ctypes.data,
-                                                        _stream_ptr()))
+                                                        self._stream()))
         return self
 
     def set_masks(self, table: Optional[np.ndarray], n_fmask: int = 0, n_tmask: int = 0,
                   mask_value: Optional[float] = None) -> "Plan":
         """``table``: int32 (B, n_fmask + n_tmask, 2) = (start, width), frequency masks first."""
         if table is None:
-            _lib.check(self._lib.js2t_plan_set_masks(self._h, 0, 0, None, 0, 0.0, _stream_ptr()))
+            _lib.check(self._lib.js2t_plan_set_masks(self._h, 0, 0, None, 0, 0.0, self._stream()))
             return self
         t = np.ascontiguousarray(table, np.int32)
         assert t.shape == (self.n_utts, n_fmask + n_tmask, 2), t.shape
         mode = _lib.MASK_VALUE_MEAN if mask_value is None else _lib.MASK_VALUE_CONST
+        # the table is pageable host memory: the C side returns once it has been staged
         _lib.check(self._lib.js2t_plan_set_masks(self._h, n_fmask, n_tmask, t.ctypes.data, mode,
                                                  0.0 if mask_value is None else float(mask_value),
-                                                 _stream_ptr()))
-        torch.cuda.current_stream().synchronize()  # table is pageable host memory
+                                                 self._stream()))
         return self
 
     # ---- execution --------------------------------------------------------------------------
@@ -226,7 +234,7 @@ class Plan:
         assert out.is_cuda and out.is_contiguous() and out.dtype == torch.float32
         assert out.numel() >= self.out_rows * NUM_MEL
         fn = self._lib.js2t_features_execute if self.feature_input else self._lib.js2t_fbank_execute
-        _lib.check(fn(self._h, src.data_ptr(), out.data_ptr(), _stream_ptr()))
+        _lib.check(fn(self._h, src.data_ptr(), out.data_ptr(), self._stream()))
         return out
 
     def set_option(self, name: str, value: int) -> "Plan":
@@ -256,19 +264,19 @@ class Plan:
         """(B, 160) float64 per-utterance sum | sum of squares of the raw log-mel (a device copy)."""
         out = torch.empty((self.n_utts, 2 * NUM_MEL), dtype=torch.float64,
                           device=f"cuda:{self.ctx.device}")
-        _lib.check(self._lib.js2t_plan_copy_utt_stats(self._h, out.data_ptr(), _stream_ptr()))
+        _lib.check(self._lib.js2t_plan_copy_utt_stats(self._h, out.data_ptr(), self._stream()))
         return out
 
     def accumulate_global(self, accum: torch.Tensor) -> None:
         """accum (161,) float64 cuda: sum[80] | sumsq[80] | frames  += this batch."""
         assert accum.is_cuda and accum.dtype == torch.float64 and accum.numel() == 2 * NUM_MEL + 1
-        _lib.check(self._lib.js2t_global_stats_accumulate(self._h, accum.data_ptr(), _stream_ptr()))
+        _lib.check(self._lib.js2t_global_stats_accumulate(self._h, accum.data_ptr(), self._stream()))
 
     def finalize_global(self, accum: torch.Tensor) -> None:
-        _lib.check(self._lib.js2t_global_stats_finalize(self._h, accum.data_ptr(), _stream_ptr()))
+        _lib.check(self._lib.js2t_global_stats_finalize(self._h, accum.data_ptr(), self._stream()))
 
     def normalize(self, out: torch.Tensor) -> torch.Tensor:
-        _lib.check(self._lib.js2t_normalize_execute(self._h, out.data_ptr(), _stream_ptr()))
+        _lib.check(self._lib.js2t_normalize_execute(self._h, out.data_ptr(), self._stream()))
         return out
 
     def split(self, out: torch.Tensor) -> List[torch.Tensor]:
@@ -410,7 +418,7 @@ def reformat_48k_to_16k(y: torch.Tensor, out: Optional[torch.Tensor] = None) -> 
     with torch.cuda.device(y.device):
         _lib.check(lib.js2t_reformat_48k_to_16k(
             ctx.handle, y.data_ptr(), int(y.dtype == torch.float32), n, out.data_ptr(),
-            ws.data_ptr(), _stream_ptr()))
+            ws.data_ptr(), _stream_ptr(device=y.device.index)))
     return out
 
 

@@ -110,8 +110,10 @@ def _get_features_from_zip(path, byte_offset, byte_size):
 def get_n_frames(wave_length: int, sample_rate: int):
     """helpers_for_audio.py:93-96: frame count estimated from the duration in whole milliseconds
     (an approximation the reference keeps for manifests; the exact count is ``tables.num_frames``)."""
-    milliseconds = int(1000 * wave_length / sample_rate)
-    return int((milliseconds - 25) / 10 + 1)
+    # the operation order is part of the contract: (N / sr) * 1000 and 1000 * N / sr round differently
+    # (16080 samples at 16 kHz: 1004 ms vs 1005 ms, i.e. 98 vs 99 frames)
+    duration_ms = int(wave_length / sample_rate * 1000)
+    return int(1 + (duration_ms - 25) / 10)
 
 
 def load_waveform(path: Path) -> Tuple[np.ndarray, int]:

@@ -6,11 +6,12 @@ Import shims that let the *unmodified* reference (``/root/reference/joeynmt``)
 run on CPU in the build container, so that
 
 * ``oracle/make_golden.py`` can generate golden vectors from the reference itself, and
-* ``tests/test_oracle_vs_reference.py`` can pin the numpy/C restatement in ``oracle/``
-  against the real thing whenever ``/root/reference`` is mounted.
-
-``/root/reference`` does not exist on the GPU box; nothing here is used by ``-m gpu`` tests,
-``smoke()`` or ``bench.py``.
+* ``tests/test_oracle.py`` can pin the numpy restatement in ``oracle/`` against the real thing, and
+* the installed copy ``oracle/_ref`` (``oracle/build_ref.sh``: ``pip install --no-deps --target``, byte-
+  identical to ``/root/reference/joeynmt``) can run on the GPU box, where ``/root/reference`` does not
+  exist: ``bench.py --impl reference`` / the ``cpu_baseline`` leg time the reference's own
+  ``extract_fbank_features`` -> ``CMVN``, and ``tests/test_gpu_reference_callers.py`` drives the
+  reference's own dataset classes with ``joeys2t_b200.install()`` patched in.
 
 Shims:
 
@@ -23,6 +24,7 @@ Shims:
   ``sacrebleu``, ``subword_nmt``, ``matplotlib``, ``editdistance``, ``plotly``.
 """
 import importlib
+import os
 import sys
 import types
 import wave
@@ -30,11 +32,29 @@ from pathlib import Path
 
 import numpy as np
 
-REFERENCE_ROOT = Path("/root/reference")
+_SOURCE_ROOT = Path("/root/reference")                     # the build container
+_INSTALLED_ROOT = Path(__file__).resolve().parent / "_ref"  # oracle/build_ref.sh (travels to the GPU box)
+
+
+def _has_reference(root: Path) -> bool:
+    return (root / "joeynmt" / "helpers_for_audio.py").is_file()
+
+
+# where ``import joeynmt`` resolves to: the mounted source tree if present, else the installed copy
+# (JS2T_USE_INSTALLED_REF=1 forces the installed copy, to rehearse the GPU-box situation here)
+REFERENCE_ROOT = _INSTALLED_ROOT if _has_reference(_INSTALLED_ROOT) and (
+    os.environ.get("JS2T_USE_INSTALLED_REF") or not _has_reference(_SOURCE_ROOT)) else _SOURCE_ROOT
 
 
 def reference_available() -> bool:
-    return (REFERENCE_ROOT / "joeynmt" / "helpers_for_audio.py").is_file()
+    return _has_reference(REFERENCE_ROOT)
+
+
+def speech_fixture_dir() -> Path:
+    """test/data/speech of the reference (ten wavs, TSVs, vocabulary)."""
+    if REFERENCE_ROOT == _SOURCE_ROOT:
+        return REFERENCE_ROOT / "test" / "data" / "speech"
+    return REFERENCE_ROOT / "test_data" / "speech"
 
 
 def load_wav_int16(path) -> np.ndarray:
@@ -78,7 +98,7 @@ def install(full_stack: bool = False):
     :returns: the imported ``joeynmt.helpers_for_audio`` module of the reference.
     """
     if not reference_available():
-        raise RuntimeError("/root/reference is not mounted; the reference cannot be imported")
+        raise RuntimeError("neither /root/reference nor oracle/_ref (oracle/build_ref.sh) holds the reference")
     import torchaudio
 
     def _apply_effects_tensor(waveform, sample_rate, effects):

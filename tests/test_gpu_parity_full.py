@@ -1,0 +1,253 @@
+# coding: utf-8
+"""
+Full-size parity of the CUDA path on BASELINE.json's own configs — EVERY utterance of configs 2, 3 and 4
+against the reference's CPU path (``oracle/ref_cpu_path``: the unmodified reference when ``oracle/_ref`` is
+installed, else torchaudio's ``kaldi.fbank`` + restated glue), computed on all host cores — plus the
+fused global-CMVN + SpecAugment epilogue (config 3's global variant) and the remaining drop-in entry
+points.  ``-m gpu`` only.
+
+Tolerances (BASELINE.json north_star / SURVEY.md §8c):
+  * raw log-mel:            max |Δ| <= 1e-3
+  * CMVN-normalised output: |Δ| <= 5e-4 + 1e-4 |ref|
+  * SpecAugment:            masked-cell positions bit-exact, fill value within 1e-6
+"""
+import argparse
+import multiprocessing as mp
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import fbank_numpy as O  # noqa: E402
+
+LOGMEL_ATOL = 1e-3
+MUSTC_SA = dict(freq_mask_n=2, freq_mask_f=27, time_mask_n=2, time_mask_t=100, time_mask_p=1.0)
+
+
+@pytest.fixture(scope="module")
+def fe():
+    if not torch.cuda.is_available():
+        pytest.fail("gpu tests need a CUDA device")
+    from joeys2t_b200 import _lib, frontend
+    if _lib.is_stale():
+        _lib.build()
+    return frontend
+
+
+def reference_logmel(waves):
+    """Raw log-mel of every utterance by the reference CPU path, one process per host core (spawned: the
+    test process holds a CUDA context and torch thread pools that must not be forked)."""
+    from oracle import ref_cpu_path
+    cores = min(os.cpu_count() or 1, 32)
+    with mp.get_context("spawn").Pool(cores, initializer=ref_cpu_path.single_thread) as pool:
+        return pool.map(ref_cpu_path.fbank, waves, chunksize=max(1, len(waves) // (4 * cores)))
+
+
+def tables_to_masks(table, nf, u):
+    fm = [(int(a), int(b)) for a, b in table[u, :nf]]
+    tm = [(int(a), int(b)) for a, b in table[u, nf:]]
+    return fm, tm
+
+
+def assert_cmvn_close(got, ref, what):
+    err = np.abs(got - ref)
+    tol = 5e-4 + 1e-4 * np.abs(ref)
+    bad = err > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())} cells out of tolerance, max err {err.max():.3e}"
+
+
+def _bench_batch(workload, seed):
+    import bench
+    return bench.make_batch(argparse.Namespace(workload=workload, utts=0, sweep_hours=0.0), seed)
+
+
+# ------------------------------------------------------------------------------------------------
+# configs 2, 3, 4 at BASELINE.json's full sizes: every utterance, every cell
+# ------------------------------------------------------------------------------------------------
+def test_config2_every_utterance_vs_reference_cpu_path(fe):
+    """256 x U(10,15) s int16 (the headline workload of bench.py, same generator and seed): raw log-mel and
+    utterance CMVN of all 256 utterances (~319 k frames)."""
+    waves = _bench_batch("cfg2", 1234)
+    assert len(waves) == 256
+    refs = reference_logmel(waves)
+    raw, nf = fe.fbank_cmvn_specaug_ragged(waves)
+    out, nf2 = fe.fbank_cmvn_specaug_ragged(waves, cmvn={})
+    raw, out = raw.cpu().numpy(), out.cpu().numpy()
+    assert nf.tolist() == [r.shape[0] for r in refs] == nf2.tolist()
+    off, worst = 0, 0.0
+    for u, ref in enumerate(refs):
+        t = ref.shape[0]
+        d = float(np.abs(raw[off:off + t] - ref).max())
+        assert d <= LOGMEL_ATOL, f"utterance {u}: log-mel max err {d:.3e}"
+        worst = max(worst, d)
+        assert_cmvn_close(out[off:off + t], O.cmvn(ref), f"utterance {u}")
+        off += t
+    assert off == raw.shape[0]
+    print(f"config 2: 256 utterances, {off} frames, worst log-mel |err| {worst:.2e}")
+
+
+@pytest.mark.parametrize("variant", ["utterance", "global"])
+def test_config3_every_utterance_with_specaugment(fe, variant):
+    """512 ragged utterances (1-30 s) + SpecAugment (configs/mustc_st.yaml:23-28): utterance CMVN with the
+    mean fill (the reference's mustc_st.yaml:29-32), and the global-CMVN extension with a constant fill —
+    the fused fbank epilogue bench.py's cfg3g times."""
+    from joeys2t_b200.data_augmentation import SpecAugment, mask_tables_for_batch
+    waves = _bench_batch("cfg3", 2345)
+    assert len(waves) == 512
+    refs = reference_logmel(waves)
+    n_frames = [r.shape[0] for r in refs]
+    np.random.seed(2345)
+    table, nfm, ntm = mask_tables_for_batch(SpecAugment(**MUSTC_SA), n_frames)
+    if variant == "utterance":
+        out, nf = fe.fbank_cmvn_specaug_ragged(waves, cmvn={}, masks=table, n_fmask=nfm, n_tmask=ntm)
+        want = [O.apply_specaugment_masks(O.cmvn(r), tables_to_masks(table, nfm, u)) for u, r in enumerate(refs)]
+    else:
+        s, q, n = O.global_cmvn_stats(refs)
+        mean = s / n
+        istd = 1.0 / np.sqrt(np.maximum(q / n - mean**2, 1e-10))
+        out, nf = fe.fbank_cmvn_specaug_ragged(waves, cmvn={}, global_stats=(mean, istd), masks=table,
+                                               n_fmask=nfm, n_tmask=ntm, mask_value=0.0)
+        want = [O.apply_specaugment_masks(g, tables_to_masks(table, nfm, u), mask_value=0.0)
+                for u, g in enumerate(O.global_cmvn(refs))]
+    assert nf.tolist() == n_frames
+    got = out.cpu().numpy()
+    off = 0
+    for u, w in enumerate(want):
+        t = n_frames[u]
+        blk = got[off:off + t]
+        off += t
+        m = np.zeros((t, 80), bool)
+        for f0, f in table[u, :nfm]:
+            m[:, f0:f0 + f] = True
+        for t0, tt in table[u, nfm:]:
+            m[t0:t0 + tt, :] = True
+        # masked cells: exactly the drawn rectangles, one fill value per utterance (bit-identical cells)
+        if m.any():
+            vals = blk[m]
+            assert np.ptp(vals) == 0.0, u
+            assert abs(float(vals[0]) - float(w[m][0])) <= 1e-6, u
+        assert_cmvn_close(blk[~m], w[~m], f"{variant} utterance {u}")
+
+
+def test_config4_every_utterance_longform_mixed_dtype(fe):
+    """64 x U(30,60) s, even utterances int16 / odd float32 in [-1, 1): the two-slot staging path."""
+    waves = _bench_batch("cfg4", 3456)
+    assert len(waves) == 64 and waves[0].dtype == np.int16 and waves[1].dtype == np.float32
+    refs = reference_logmel(waves)
+    raw, nf = fe.fbank_cmvn_specaug_ragged(waves)
+    out, _ = fe.fbank_cmvn_specaug_ragged(waves, cmvn={})
+    raw, out = raw.cpu().numpy(), out.cpu().numpy()
+    assert nf.tolist() == [r.shape[0] for r in refs]
+    off = 0
+    for u, ref in enumerate(refs):
+        t = ref.shape[0]
+        assert np.abs(raw[off:off + t] - ref).max() <= LOGMEL_ATOL, u
+        # the reference CMVN's own float32 accumulation error grows to ~1.3e-4 at these lengths
+        # (SURVEY.md §8c); the float64 restatement of the same formula is the arbiter
+        assert_cmvn_close(out[off:off + t], O.cmvn_fp64(ref), f"utterance {u}")
+        off += t
+
+
+# ------------------------------------------------------------------------------------------------
+# fused global CMVN + SpecAugment epilogue (kEpiNormKnown) and Plan.normalize with masks
+# ------------------------------------------------------------------------------------------------
+def _global_setup(fixtures_pcm, ref_fbank, mixed):
+    pcm, _ = fixtures_pcm
+    waves = [x.astype(np.float32) / np.float32(32768.0) if (mixed and i % 2) else x for i, x in enumerate(pcm)]
+    s, q, n = O.global_cmvn_stats(ref_fbank)
+    mean = s / n
+    istd = 1.0 / np.sqrt(np.maximum(q / n - mean**2, 1e-10))
+    return waves, mean, istd, O.global_cmvn(ref_fbank)
+
+
+@pytest.mark.parametrize("layout", ["ragged", "padded"])
+@pytest.mark.parametrize("n_f,n_t", [(2, 2), (4, 12), (5, 14)])
+def test_global_cmvn_with_constant_fill_masks(fe, fixtures_pcm, ref_fbank, layout, n_f, n_t):
+    """global statistics known + masks + constant fill: <= 16 masks run in the fbank epilogue (single
+    pass), more take the three-kernel path (capi.cu run_pipeline) — both against
+    O.global_cmvn + O.apply_specaugment_masks (settings of configs/mustc_st.yaml:23-32)."""
+    from joeys2t_b200.data_augmentation import SpecAugment, mask_tables_for_batch
+    waves, mean, istd, want = _global_setup(fixtures_pcm, ref_fbank, mixed=True)
+    n_frames = [f.shape[0] for f in ref_fbank]
+    np.random.seed(7 + n_f)
+    sa = SpecAugment(freq_mask_n=n_f, freq_mask_f=27, time_mask_n=n_t, time_mask_t=100, time_mask_p=1.0)
+    table, nfm, ntm = mask_tables_for_batch(sa, n_frames)
+    fill = -0.25
+    out, nf = fe.fbank_cmvn_specaug_ragged(waves, cmvn={}, global_stats=(mean, istd), masks=table, n_fmask=nfm,
+                                           n_tmask=ntm, mask_value=fill, layout=layout)
+    got = out.cpu().numpy()
+    off = 0
+    for u, g in enumerate(want):
+        t = n_frames[u]
+        blk = got[u, :t] if layout == "padded" else got[off:off + t]
+        off += t
+        ref = O.apply_specaugment_masks(g, tables_to_masks(table, nfm, u), mask_value=fill)
+        m = ref != g  # cells the oracle filled (a cell already equal to the fill value stays equal)
+        assert (blk[m] == np.float32(fill)).all(), u
+        assert_cmvn_close(blk[~m], ref[~m], f"utterance {u}")
+        if layout == "padded":
+            assert (got[u, t:] == 1.0).all()
+
+
+@pytest.mark.parametrize("fill", [None, 0.5])
+def test_two_pass_normalize_with_masks(fe, fixtures_pcm, ref_fbank, fill):
+    """STATS_ONLY pass -> global finalize -> Plan.normalize (js2t_normalize_execute) with masks: mean fill
+    (= mean of the globally normalised utterance, data_augmentation.py:45-46) and constant fill."""
+    from joeys2t_b200 import distributed as D
+    from joeys2t_b200.data_augmentation import SpecAugment, mask_tables_for_batch
+    waves, _, _, want = _global_setup(fixtures_pcm, ref_fbank, mixed=False)
+    n_frames = [f.shape[0] for f in ref_fbank]
+    np.random.seed(11)
+    table, nfm, ntm = mask_tables_for_batch(SpecAugment(**MUSTC_SA), n_frames)
+    packed = fe.PackedPCM(waves)
+    plan = fe.Plan(packed.n_samples, packed.byte_off, packed.is_f32)
+    plan.set_cmvn("stats")
+    raw = plan.execute(packed.to_device())
+    accum = D.new_accumulator("cuda")
+    plan.accumulate_global(accum)
+    plan.set_cmvn("global")
+    plan.finalize_global(accum)
+    plan.set_masks(table, nfm, ntm, mask_value=fill)
+    got = plan.normalize(raw).cpu().numpy()
+    torch.cuda.synchronize()
+    plan.close()
+    off = 0
+    for u, g in enumerate(want):
+        t = n_frames[u]
+        blk = got[off:off + t]
+        off += t
+        ref = O.apply_specaugment_masks(g, tables_to_masks(table, nfm, u), mask_value=fill)
+        m = np.zeros((t, 80), bool)
+        for f0, f in table[u, :nfm]:
+            m[:, f0:f0 + f] = True
+        for t0, tt in table[u, nfm:]:
+            m[t0:t0 + tt, :] = True
+        if m.any():
+            assert np.ptp(blk[m]) == 0.0
+            want_fill = float(g.mean()) if fill is None else fill
+            assert abs(float(blk[m][0]) - want_fill) <= (2e-5 if fill is None else 0.0), u
+        assert_cmvn_close(blk[~m], ref[~m], f"utterance {u}")
+
+
+# ------------------------------------------------------------------------------------------------
+# remaining drop-in entry points
+# ------------------------------------------------------------------------------------------------
+def test_get_torchaudio_fbank_takes_int16_range_floats(fe, fixtures_pcm, ref_fbank):
+    """helpers_for_audio.py:30-37: the reference calls it with the waveform already scaled by 2**15
+    (helpers_for_audio.py:54); the drop-in undoes that scaling exactly before the device path."""
+    from joeys2t_b200.helpers_for_audio import _get_torchaudio_fbank, extract_fbank_features
+    pcm, _ = fixtures_pcm
+    for i in (0, 6):
+        scaled = torch.from_numpy(pcm[i].astype(np.float32))[None]  # == (int16 / 32768) * 2**15
+        got = _get_torchaudio_fbank(scaled, 16000, n_bins=80)
+        assert got.dtype == np.float32 and got.shape == ref_fbank[i].shape
+        assert np.abs(got - ref_fbank[i]).max() <= LOGMEL_ATOL
+        # same bits as the public entry point on the unscaled waveform
+        direct = extract_fbank_features(scaled * 2.0**-15, 16000)
+        assert np.array_equal(got, direct)
+    with pytest.raises(ValueError):
+        _get_torchaudio_fbank(torch.zeros(1, 1000), 8000)
