@@ -21,12 +21,22 @@ scaling).  A "step" is one pass of the hot path (fbank -> utterance CMVN) over o
                 event between two kernels would undo; the events are therefore recorded in a second
                 region of the same ``steps`` steps right after the timed one, and that region's own
                 (slower) step time is reported next to them
-* ``cpu_baseline``  the reference's CPU path (torchaudio's kaldi.fbank + restated glue / CMVN, or the
-                numpy restatement if torchaudio is missing) on all host cores
-* ``--impl reference``  times that CPU path alone and prints the same JSON line
+* ``roofline_fp32``  the same kernel against the FP32 pipe, from the ncu counters of THIS build
+                (profiles/fbank_ncu_metrics.json, keyed by a hash of the kernel sources; null when
+                the committed capture belongs to another build)
+* ``cpu_baseline``  the reference's CPU path on all host cores: the UNMODIFIED reference
+                (joeynmt.helpers_for_audio.extract_fbank_features -> joeynmt.data_augmentation.CMVN,
+                installed into oracle/_ref by oracle/build_ref.sh) when available — kind
+                "reference" — else torchaudio's kaldi.fbank + restated glue / CMVN — kind "port"
+* ``--impl reference``  times that CPU path alone, the whole batch per step, same JSON line
+* ``cfg5``      (N > 1 only) a short corpus sweep with global CMVN whose statistics are unknown: the
+                path's one collective (161 x fp64 all-reduce through the C ABI's ncclAllReduce), with
+                on-box checks that every rank ends up with the same statistics and that they equal a
+                rank-0 float64 recomputation from all ranks' per-utterance statistics
 
-Between timed steps the working set rotates over ``--rotate`` distinct batches so that inputs and
-outputs (~205 MB per batch) exceed the 126 MB L2.
+Between timed steps the working set rotates over enough batch buffers (inputs + outputs ~205 MB per
+batch) to exceed 4 GB, far beyond the 126 MB L2: ``--rotate`` distinct synthetic batches, replicated
+into distinct device buffers (the kernels are data-independent; what matters for L2 is the address).
 """
 import argparse
 import json
@@ -58,7 +68,11 @@ def parse_args():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
                     help="BASELINE.json config; cfg2 is the headline, the others are extra measurement rows")
     ap.add_argument("--sweep-hours", type=float, default=1000.0, help="cfg5: corpus size in audio-hours")
-    ap.add_argument("--rotate", type=int, default=4, help="distinct batches cycled through (L2 flush)")
+    ap.add_argument("--rotate", type=int, default=4, help="distinct synthetic batches generated per rank")
+    ap.add_argument("--working-set-gb", type=float, default=4.2,
+                    help="device buffers cycled through between timed steps (inputs + outputs), >> L2")
+    ap.add_argument("--cfg5-leg-hours", type=float, default=48.0,
+                    help="N > 1: size of the attached config-5 sweep in audio-hours (0 disables)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -69,7 +83,9 @@ WORKLOADS = {
     "cfg1": dict(utts=10, cmvn="utterance", name="test/data fixture clips (10 wavs, 1.7-14.7 s, int16) + utterance CMVN"),
     "cfg2": dict(utts=256, cmvn="utterance",
                  name="librispeech_100h-shaped synthetic batch: {utts} x U(10,15) s 16 kHz int16 utterances, "
-                      "80-bin Kaldi fbank + utterance CMVN"),
+                      "80-bin Kaldi fbank + utterance CMVN (generator: joeys2t_b200.synthetic.pooled_batch, "
+                      "seed 1234 + 1000 rank + batch — SURVEY 8d's envelope x pink-noise 'speech' cut from one "
+                      "90 s pool with per-utterance gain; the kernels are data-independent)"),
     "cfg3": dict(utts=512, cmvn="utterance", masks=True,
                  name="mustc_st-shaped ragged batch: {utts} x lognormal(median 5 s, 1-30 s) int16, utterance CMVN + "
                       "SpecAugment (2 freq masks F=27, 2 time masks T=100)"),
@@ -82,6 +98,13 @@ WORKLOADS = {
                  name="{hours:.0f}-hour synthetic corpus sweep (librispeech-shaped int16 batches cycled), global CMVN with "
                       "unknown statistics: pass 1 statistics -> all-reduce of 161 fp64 -> pass 2 normalised fbank"),
 }
+
+
+def bench_config(args):
+    """`config` of the JSON line — identical in both arms (the driver compares them)."""
+    w = WORKLOADS[args.workload]
+    return {"workload": workload_name(args), "baseline_config": args.workload,
+            "utterances_per_step": args.utts or w["utts"], "cmvn": w["cmvn"]}
 
 
 def workload_name(args):
@@ -133,6 +156,12 @@ def cpu_kind():
     return ref_cpu_path.KIND
 
 
+def cpu_kind_tag():
+    """"reference" (unmodified joeynmt from /root/reference or oracle/_ref) or "port"."""
+    from oracle import ref_cpu_path
+    return ref_cpu_path.KIND_TAG
+
+
 def cpu_port_throughput(waves, cores, budget_s=12.0):
     """audio-hours/sec of the reference CPU path over ``waves`` with a pool of ``cores`` processes,
     repeated until about ``budget_s`` seconds of wall time have been measured."""
@@ -154,9 +183,10 @@ def cpu_port_throughput(waves, cores, budget_s=12.0):
 
 
 def cpu_sample(waves, cores):
-    """Bounded sample of the workload: a whole batch when it is small enough."""
-    n = min(len(waves), max(cores * 8, 64))
-    return waves[:n]
+    """The whole batch: one step of the reference arm is the same 256 utterances as one GPU step
+    (0.887 audio-h take ~0.15 s on 16 cores, so nothing needs to be sub-sampled)."""
+    del cores
+    return waves
 
 
 # ----------------------------------------------------------------------------------------------
@@ -220,13 +250,20 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
 
 
-def measured_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
-    p = ROOT / "profiles" / "fbank_dram_traffic.json"
+def build_metrics():
+    """ncu counters of the dominant kernel for THE BUILD BEING MEASURED: profiles/fbank_ncu_metrics.json is
+    written by tools/ncu_summary.py --json from one `ncu --set full` capture and carries a hash of the kernel
+    sources; a capture of another build is not attached (returns None and the reason)."""
+    from joeys2t_b200 import _lib
+    p = ROOT / "profiles" / "fbank_ncu_metrics.json"
     try:
-        return json.loads(p.read_text())
+        m = json.loads(p.read_text())
     except Exception:  # pylint: disable=broad-except
-        return None
+        return None, "profiles/fbank_ncu_metrics.json missing"
+    sha = _lib.kernel_source_sha16()
+    if m.get("source_sha16") != sha:
+        return None, f"profiles/fbank_ncu_metrics.json belongs to build {m.get('source_sha16')}, this is {sha}"
+    return m, f"profiles/fbank_ncu_metrics.json ({m.get('report')}, build {sha})"
 
 
 def measured_peaks():
@@ -276,14 +313,14 @@ def run_reference(args):
                 break
     dt = float(np.mean(times))
     value = hours / dt
-    sample_desc = (f"{len(sample)} of the {len(waves)} utterances of one batch ({hours:.3f} audio-h) per step, "
-                   f"{cores} processes x 1 thread; {cpu_kind()}")
+    sample_desc = (f"all {len(sample)} utterances of one batch ({hours:.3f} audio-h) per step, "
+                   f"{cores} processes x 1 thread ({cpu_model()}); {cpu_kind()}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(times), "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "cpu_model": cpu_model()},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "config": bench_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": cpu_kind_tag(),
                          "sample": sample_desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -305,7 +342,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    from joeys2t_b200 import _lib, distributed, frontend, synthetic
+    from joeys2t_b200 import _lib, distributed, frontend
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
@@ -322,7 +359,14 @@ def run_b200(args):
             dist.barrier()
 
     if args.workload == "cfg5":
-        return run_sweep(args, rank, local_rank, world, dev)
+        res = sweep_measure(args, rank, local_rank, world, dev, args.sweep_hours,
+                            recompute=bool(os.environ.get("JS2T_SWEEP_RECOMPUTE")), comm=None)
+        if rank == 0:
+            print(json.dumps(sweep_line(args, world, res)), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     # ---- synthetic workload: `rotate` distinct batches per rank, resident in HBM ----------------
     from joeys2t_b200.data_augmentation import SpecAugment, mask_tables_for_batch
@@ -360,6 +404,21 @@ def run_b200(args):
     torch.cuda.synchronize()
     hours_per_step = [sum(len(w) for w in b) / SR / 3600.0 for b in batches]
     frames_per_step = [p.total_frames for p in plans]
+    # L2 (126 MB) must not help between timed steps: every step uses its own input AND output buffers out of
+    # a ring whose total size exceeds --working-set-gb (>= 4 GB).  The R distinct synthetic batches
+    # are replicated into distinct device buffers — the kernels are data-independent, for the caches only
+    # the addresses matter — and each buffer keeps the plan (geometry) of the batch it holds.
+    per_batch = float(np.mean([p.nbytes for p in packs]) + np.mean([o.numel() * 4 for o in outs]))
+    n_buf = max(R, int(np.ceil(args.working_set_gb * 1e9 / per_batch)))
+    n_buf = min(n_buf, max(R, int(0.5 * torch.cuda.mem_get_info(dev)[0] / per_batch)))
+    for k in range(R, n_buf):
+        pcm_dev.append(pcm_dev[k % R].clone())
+        outs.append(torch.empty_like(outs[k % R]))
+    torch.cuda.synchronize()
+    working_set = sum(t.numel() for t in pcm_dev) + 4 * sum(o.numel() for o in outs)
+
+    def step(i):
+        plans[i % n_buf % R].execute(pcm_dev[i % n_buf], outs[i % n_buf])
 
     def barrier():
         torch.cuda.synchronize()
@@ -368,8 +427,8 @@ def run_b200(args):
             torch.cuda.synchronize()
 
     # ---- device-resident timing ------------------------------------------------------------------
-    for i in range(args.warmup):
-        plans[i % R].execute(pcm_dev[i % R], outs[i % R])
+    for i in range(max(args.warmup, 3)):
+        step(i)
     clocks = ClockSampler(local_rank)
     barrier()
     clocks.start()
@@ -380,28 +439,39 @@ def run_b200(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(args.steps):
-        plans[i % R].execute(pcm_dev[i % R], outs[i % R])
+        step(i)
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     # (B) same steps again with CUDA events around the fbank kernel (recorded by the library on the
     # launching stream)
     for p in plans:
-        p.enable_profiling((args.steps + R - 1) // R)
+        p.enable_profiling((args.steps + R - 1) // R + 1)
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2.record()
     for i in range(args.steps):
-        plans[i % R].execute(pcm_dev[i % R], outs[i % R])
+        step(i)
     ev3.record()
     barrier()
     clk = clocks.stop()
     ms_total_events = ev2.elapsed_time(ev3)
-    hours_done = sum(hours_per_step[i % R] for i in range(args.steps))
-    frames_done = sum(frames_per_step[i % R] for i in range(args.steps))
-    kt = np.concatenate([p.kernel_times_ms((args.steps + R - 1) // R) for p in plans])
+    hours_done = sum(hours_per_step[i % n_buf % R] for i in range(args.steps))
+    frames_done = sum(frames_per_step[i % n_buf % R] for i in range(args.steps))
+    kt = np.concatenate([p.kernel_times_ms((args.steps + R - 1) // R + 1) for p in plans])
     kernel_ms = float(kt.mean())
     for p in plans:
         p.enable_profiling(0)
+    # (C) a longer region (>= 50 ms of device time, same loop) — the driver's --steps 20 region is ~4 ms,
+    # this one shows that the short region is representative
+    long_steps = max(args.steps, int(np.ceil(60.0 / max(ms_total / args.steps, 1e-3))))
+    ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev4.record()
+    for i in range(long_steps):
+        step(i)
+    ev5.record()
+    barrier()
+    ms_long = ev4.elapsed_time(ev5)
+    hours_long = sum(hours_per_step[i % n_buf % R] for i in range(long_steps))
 
     # ---- end to end: pinned host PCM -> device -> features -> pinned host -------------------------
     e2e = None
@@ -432,17 +502,24 @@ def run_b200(args):
         barrier()
         e2e_ms = e0.elapsed_time(e1)
         assert np.isfinite(checksum)
-        e2e = (hours_done, e2e_ms, int(np.mean([p.nbytes for p in packs])),
-               int(np.mean([o.numel() * 4 for o in outs])))
+        e2e_hours = sum(hours_per_step[i % R] for i in range(args.steps))
+        e2e = (e2e_hours, e2e_ms, int(np.mean([p.nbytes for p in packs])),
+               int(np.mean([plans[j].out_rows * 80 * 4 for j in range(R)])))
 
     # ---- reduce over ranks: max time, summed work ---------------------------------------------------
-    t = torch.tensor([ms_total, e2e[1] if e2e else 0.0], dtype=torch.float64, device=dev)
-    w = torch.tensor([hours_done, float(frames_done)], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e[1] if e2e else 0.0, ms_long], dtype=torch.float64, device=dev)
+    w = torch.tensor([hours_done, float(frames_done), e2e[0] if e2e else 0.0, hours_long],
+                     dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
-    ms_total_max, e2e_ms_max = t.tolist()
-    hours_all, frames_all = w.tolist()
+    ms_total_max, e2e_ms_max, ms_long_max = t.tolist()
+    hours_all, frames_all, e2e_hours_all, hours_long_all = w.tolist()
+
+    # ---- N > 1: the path's one collective, in front of the driver ------------------------------------
+    cfg5 = None
+    if world > 1 and args.cfg5_leg_hours > 0:
+        cfg5 = cfg5_leg(args, rank, local_rank, world, dev)
 
     if rank == 0:
         value = hours_all / (ms_total_max * 1e-3)
@@ -450,53 +527,65 @@ def run_b200(args):
         frames_launch = float(np.mean(frames_per_step))
         algo_bytes = float(np.mean([algorithmic_bytes(pk, pl) for pk, pl in zip(packs, plans)]))
         achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
+        metrics, metrics_src = build_metrics() if args.workload == "cfg2" else (None, "captured on cfg2 only")
+        sm_mhz = (clk or {}).get("sm_mhz") or 1965.0
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total_max / args.steps, "higher_is_better": True,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": workload_name(args), "baseline_config": args.workload,
+            "config": bench_config(args),
+            "details": {
                 "frames_per_step_per_gpu": frames_launch,
                 "audio_hours_per_step_per_gpu": float(np.mean(hours_per_step)),
                 "pcm": "resident in HBM", "cmvn": wl["cmvn"] + " (norm_means, norm_vars, before)",
                 "cmvn_path": "fbank epilogue" if wl["cmvn"] == "global" else "fbank+stats, finalize, apply kernels",
-                "l2": f"rotating over {R} distinct batches per GPU "
-                      f"(~{R * (np.mean([p.nbytes for p in packs]) + np.mean([o.numel()*4 for o in outs])) / 1e6:.0f} MB "
-                      "of inputs+outputs, larger than the 126 MB L2)",
-                "parallelism": f"utterance-sharded x{world}, no data-path collective",
+                "l2": f"every step uses its own input and output buffers out of a ring of {n_buf} "
+                      f"({working_set / 1e9:.2f} GB of inputs+outputs per GPU, >> the 126 MB L2; {R} distinct "
+                      "synthetic batches replicated into distinct device buffers)",
+                "working_set_bytes_per_gpu": int(working_set),
+                "parallelism": f"utterance-sharded x{world}, no data-path collective in this workload",
+                "long_region": {"steps": long_steps, "ms": ms_long_max,
+                                "value": hours_long_all / (ms_long_max * 1e-3),
+                                "note": "same loop over >= 60 ms of device time (the timed region of `value` "
+                                        "is the contract's K steps)"},
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
-                "traffic": (measured_traffic() or {}).get("dram_bytes_per_launch") if args.workload == "cfg2" else None,
-                "traffic_source": (measured_traffic() or {}).get("source") if args.workload == "cfg2" else None,
+                "traffic": (metrics or {}).get("dram_bytes_per_launch"),
+                "traffic_source": metrics_src,
                 "kernel": "fbank_tile_kernel", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "peak_source": peak_src,
                 "kernel_share_of_step": kernel_ms / (ms_total_events / args.steps),
                 "ms_per_step_with_kernel_events": ms_total_events / args.steps,
+                "working_set_bytes": int(working_set),
                 "how": "kernel_ms = mean of CUDA-event pairs recorded by the library around every fbank "
                        "launch on the launching stream, in a second region of the same `steps` steps right "
                        "after the timed one (events between kernels defeat the programmatic dependent "
                        "launch that chains the step's three kernels, so that region's steps are slower)",
-                "note": "the kernel is bound by latency hiding at 16 resident warps (FMA pipe 49 %, issue 55 %, "
-                        "LSU 63 % busy), not by HBM; see DESIGN.md and profiles/",
             },
+            "roofline_fp32": fp32_roofline(metrics, metrics_src, frames_launch, kernel_ms, sm_mhz, n_sm),
             "clocks": clk,
             "gpu_launches": ((2 if wl.get("masks") else 1) if wl["cmvn"] == "global" else 3) * args.steps,
         }
         if e2e:
-            line["e2e"] = {"value": hours_all / (e2e_ms_max * 1e-3), "unit": UNIT,
+            line["e2e"] = {"value": e2e_hours_all / (e2e_ms_max * 1e-3), "unit": UNIT,
                            "h2d_bytes_per_step": e2e[2], "d2h_bytes_per_step": e2e[3],
+                           "gbs_per_direction_per_gpu": max(e2e[2], e2e[3]) * args.steps / (e2e_ms_max * 1e-3) / 1e9,
+                           "host_ceiling_gbs": host_ceiling(),
                            "host_thread_bound_to_gpu_numa_node": bool(numa_bound)}
+        if cfg5 is not None:
+            line["cfg5"] = cfg5
         if not args.no_cpu_baseline and world == 1:
             os.sched_setaffinity(0, orig_affinity)  # the CPU baseline gets every core back
             cores = os.cpu_count() or 1
             sample = cpu_sample(batches[0], cores)
             v, dt, passes = cpu_port_throughput(sample, cores)
             line["cpu_baseline"] = {
-                "value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"{len(sample)} of {len(batches[0])} utterances of one batch x {passes} passes, "
+                "value": v, "unit": UNIT, "cores": cores, "kind": cpu_kind_tag(),
+                "sample": f"all {len(sample)} utterances of one batch x {passes} passes, "
                           f"{dt:.1f} s wall on {cores} processes x 1 thread ({cpu_model()}); {cpu_kind()}"}
         print(json.dumps(line), flush=True)
     for p in plans:
@@ -506,7 +595,77 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def run_sweep(args, rank, local_rank, world, dev):
+def fp32_roofline(metrics, metrics_src, frames_launch, kernel_ms, sm_mhz, n_sm):
+    """The FP32 side of the roofline (the expected binding roof).  `achieved` = FP32 lane operations
+    per second from the LIVE kernel time of this run x the per-frame lane-operation count of this build's
+    SASS (ncu opcode mix); `peak` = n_sm x 128 lanes x the SM clock sampled during the run.  fma_pipe_frac /
+    issue_frac are ncu's own pipe-busy and issue-slot fractions of the same build (cold-cache capture)."""
+    out = {"source": metrics_src, "fma_pipe_frac": None, "issue_frac": None, "lane_ops_per_frame": None,
+           "achieved": None, "peak": n_sm * 128 * sm_mhz * 1e6 / 1e12, "unit": "T lane-op/s", "frac": None}
+    if metrics:
+        lane = metrics.get("lane_ops_per_frame")
+        out.update(fma_pipe_frac=metrics.get("fma_pipe_frac"), issue_frac=metrics.get("issue_frac"),
+                   lsu_wavefront_frac=metrics.get("lsu_wavefront_frac"), lane_ops_per_frame=lane,
+                   warp_inst_per_frame=metrics.get("warp_inst_per_frame"))
+        if lane:
+            out["achieved"] = lane * frames_launch / (kernel_ms * 1e-3) / 1e12
+            out["frac"] = out["achieved"] / out["peak"]
+    return out
+
+
+def host_ceiling():
+    """Aggregate pinned-memory copy bandwidth of this box measured by tools/h2d_probe.py (committed under
+    profiles/): what bounds the host-resident (e2e) path as GPUs are added."""
+    p = ROOT / "profiles" / "h2d_probe.json"
+    try:
+        return json.loads(p.read_text())
+    except Exception:  # pylint: disable=broad-except
+        return None
+
+
+def cfg5_leg(args, rank, local_rank, world, dev):
+    """N > 1: a short config-5 sweep (global CMVN with unknown statistics) attached to the headline line, so
+    that the path's one exchange step — the all-reduce of 161 float64 — runs under the driver's own
+    scaling run, with on-box checks of what it produced.  Both pass-2 strategies are run."""
+    import torch
+    import torch.distributed as dist
+
+    from joeys2t_b200 import distributed
+    impl = "js2t_global_stats_allreduce (C ABI -> ncclAllReduce on a communicator from js2t_nccl_comm_create)"
+    comm = None
+    try:
+        comm = distributed.NcclCommunicator(local_rank)
+    except Exception as err:  # pylint: disable=broad-except
+        impl = f"torch.distributed.all_reduce (C-ABI communicator unavailable: {err})"
+    flag = torch.tensor([1.0 if comm is not None else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if flag.item() < 1.0 and comm is not None:  # all ranks or none
+        comm.close()
+        comm = None
+        impl = "torch.distributed.all_reduce (C-ABI communicator unavailable on another rank)"
+    sub = argparse.Namespace(**vars(args))
+    sub.workload, sub.rotate = "cfg5", min(args.rotate, 2)
+    out = {"workload": WORKLOADS["cfg5"]["name"].format(hours=args.cfg5_leg_hours), "allreduce_impl": impl}
+    for name, recompute in (("retain", False), ("recompute", True)):
+        res = sweep_measure(sub, rank, local_rank, world, dev, args.cfg5_leg_hours, recompute=recompute, comm=comm)
+        if rank == 0:
+            peak, _ = measured_peaks()
+            out[name] = {"value": res["value"], "unit": UNIT, "ms": res["ms"], "frac": res["achieved"] / peak,
+                         "bytes_per_frame": res["bytes_per_frame"], "corpus_hours": res["hours"],
+                         "frames": res["frames"]}
+            out["stats_check"] = {**out.get("stats_check", {}), name: res["check"]}
+            out["allreduce_us"] = res["allreduce_us"]
+            out["ranks"] = res["ranks_seen"]
+    if rank == 0:
+        out["value"] = out["retain"]["value"]
+        out["frac"] = out["retain"]["frac"]
+        out["stats_check"]["ok"] = all(v.get("ok") for v in out["stats_check"].values() if isinstance(v, dict))
+    if comm is not None:
+        comm.close()
+    return out if rank == 0 else None
+
+
+def sweep_measure(args, rank, local_rank, world, dev, hours_total, recompute, comm):
     """cfg5: corpus sweep sharded over the ranks with global CMVN whose statistics are NOT known:
     pass 1 = fbank + per-utterance statistics, accumulated on the device in fp64; one all-reduce of
     161 float64 over NCCL (the path's only collective); pass 2 normalises.  Two strategies for pass 2:
@@ -515,29 +674,31 @@ def run_sweep(args, rank, local_rank, world, dev):
       1000 h over 8 GPUs is 14 GB each): pass 1 keeps the raw log-mel of the whole share on the device
       and pass 2 normalises it in place with the apply kernel.  1 280 algorithmic bytes per frame, but
       the fbank kernel — bound by FP32 issue / latency, not HBM — runs once instead of twice;
-    * recompute (JS2T_SWEEP_RECOMPUTE=1, or the share does not fit): pass 2 runs the fbank kernel
-      again with the normalisation fused into its epilogue: 960 bytes per frame, twice the arithmetic.
+    * recompute (or the share does not fit): pass 2 runs the fbank kernel again with the normalisation
+      fused into its epilogue: 960 bytes per frame, twice the arithmetic.
 
-    The resident PCM batches are cycled until sweep_hours / world have been processed by this rank."""
+    The resident PCM batches are cycled until hours_total / world have been processed by this rank.
+    After the timed sweep the statistics are checked ON THE BOX: the frame count in acc[160] equals the
+    number of frames all ranks processed; mean / 1/std are bit-identical on every rank; and they equal a
+    rank-0 float64 recomputation from every rank's per-utterance statistics."""
     import torch
     import torch.distributed as dist
 
     from joeys2t_b200 import distributed, frontend
     R = max(1, args.rotate)
-    plans, pcm_dev, outs, packs, hours = [], [], [], [], []
+    plans, pcm_dev, outs, hours = [], [], [], []
     for r in range(R):
         waves = make_batch(args, 4567 + 1000 * rank + r)
         packed = frontend.PackedPCM(waves)
         plans.append(frontend.Plan(packed.n_samples, packed.byte_off, packed.is_f32, device=local_rank))
-        packs.append(packed)
         pcm_dev.append(packed.to_device(dev))
         outs.append(plans[-1].empty_output())
         hours.append(sum(len(w) for w in waves) / SR / 3600.0)
-    n_steps = int(np.ceil(args.sweep_hours / world / float(np.mean(hours))))
+    n_steps = max(1, int(np.ceil(hours_total / world / float(np.mean(hours)))))
     rows = [p.out_rows for p in plans]
     share_bytes = sum(rows[i % R] for i in range(n_steps)) * 80 * 4
     free_bytes = torch.cuda.mem_get_info(dev)[0]
-    retain = not os.environ.get("JS2T_SWEEP_RECOMPUTE") and share_bytes < 0.8 * free_bytes
+    retain = not recompute and share_bytes < 0.8 * free_bytes
     store, views = None, []
     if retain:
         store = torch.empty(share_bytes // 4, dtype=torch.float32, device=dev)
@@ -553,14 +714,17 @@ def run_sweep(args, rank, local_rank, world, dev):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def sweep(n):
+    def sweep(n, keep_stats=None):
         acc = distributed.new_accumulator(dev)
         for p in plans:
             p.set_cmvn("stats")
         for i in range(n):                                   # pass 1: raw log-mel + statistics
             plans[i % R].execute(pcm_dev[i % R], views[i] if retain else outs[i % R])
             plans[i % R].accumulate_global(acc)
-        distributed.allreduce_global_stats(acc)              # the one collective (161 x fp64)
+            if keep_stats is not None:
+                keep_stats.append(plans[i % R].utt_stats())
+        local = acc.clone() if keep_stats is not None else None
+        distributed.allreduce_global_stats(acc, comm=comm)   # the one collective (161 x fp64)
         for p in plans:
             p.finalize_global(acc)
         if retain:
@@ -571,15 +735,15 @@ def run_sweep(args, rank, local_rank, world, dev):
                 p.set_cmvn("global", True, True, True)
             for i in range(n):                               # pass 2: fbank again, normalised in the epilogue
                 plans[i % R].execute(pcm_dev[i % R], outs[i % R])
-        return acc
+        return acc, local
 
-    sweep(max(args.warmup, 3))
+    sweep(min(n_steps, max(args.warmup, 3)))
     clocks = ClockSampler(local_rank)
     barrier()
     clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    acc = sweep(n_steps)
+    acc, _ = sweep(n_steps)
     ev1.record()
     barrier()
     clk = clocks.stop()
@@ -587,42 +751,99 @@ def run_sweep(args, rank, local_rank, world, dev):
     hours_done = sum(hours[i % R] for i in range(n_steps))
     frames_done = sum(plans[i % R].total_frames for i in range(n_steps))
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    w = torch.tensor([hours_done, float(frames_done)], dtype=torch.float64, device=dev)
+    w = torch.tensor([hours_done, float(frames_done), 1.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
+
+    # ---- on-box checks of the exchange step (untimed): a second, instrumented sweep ------------------
+    stats = []
+    acc2, local = sweep(n_steps, keep_stats=stats)
+    torch.cuda.synchronize()
+    mine = torch.stack(stats).sum(dim=(0, 1))                       # (160,) fp64 from the per-utterance statistics
+    mine = torch.cat([mine, torch.tensor([float(frames_done)], dtype=torch.float64, device=dev)])
+    gm = plans[0].global_mean_istd()                  # (160,) float32 mean | 1/std on this rank
+    if world > 1:
+        all_acc = [torch.empty_like(acc2) for _ in range(world)]
+        all_local = [torch.empty_like(mine) for _ in range(world)]
+        all_gm = [torch.empty_like(gm) for _ in range(world)]
+        dist.all_gather(all_acc, acc2)
+        dist.all_gather(all_local, mine)
+        dist.all_gather(all_gm, gm)
+    else:
+        all_acc, all_local, all_gm = [acc2], [mine], [gm]
+    # timing of the collective itself (CUDA events around 20 back-to-back all-reduces of a scratch vector)
+    scratch = distributed.new_accumulator(dev)
+    distributed.allreduce_global_stats(scratch, comm=comm)
+    barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(20):
+        distributed.allreduce_global_stats(scratch, comm=comm)
+    a1.record()
+    torch.cuda.synchronize()
+    allreduce_us = a0.elapsed_time(a1) * 1e3 / 20
+    res = None
     if rank == 0:
-        peak, peak_src = measured_peaks()
         ms_max = float(t[0])
-        hours_all, frames_all = w.tolist()
+        hours_all, frames_all, ranks_seen = w.tolist()
+        total = torch.stack(all_local).sum(0).cpu().numpy()             # rank-0 fp64 recomputation
+        got = acc2.cpu().numpy()
+        rel = float(np.max(np.abs(got[:160] - total[:160]) / np.maximum(np.abs(total[:160]), 1e-300)))
+        n = total[160]
+        mu = total[:80] / n
+        istd = 1.0 / np.sqrt(np.maximum(total[80:160] / n - mu**2, 1e-10))
+        want = np.concatenate([mu, istd]).astype(np.float32)
+        mine_gm = all_gm[0].cpu().numpy()
+        check = {
+            "frames_in_acc160": float(got[160]), "frames_processed_all_ranks": float(frames_all),
+            "frame_count_exact": bool(got[160] == frames_all == n),
+            "acc_identical_on_all_ranks": bool(all(torch.equal(a, all_acc[0]) for a in all_acc)),
+            "mean_istd_bit_identical_on_all_ranks": bool(all(torch.equal(g, all_gm[0]) for g in all_gm)),
+            "max_rel_err_vs_rank0_fp64_recomputation": rel,
+            "mean_istd_max_abs_err_vs_recomputation": float(np.max(np.abs(mine_gm - want))),
+        }
+        check["ok"] = bool(check["frame_count_exact"] and check["acc_identical_on_all_ranks"] and
+                           check["mean_istd_bit_identical_on_all_ranks"] and rel <= 1e-12 and
+                           check["mean_istd_max_abs_err_vs_recomputation"] <= 1e-6)
         # recompute: 960 B/frame (PCM read twice, features written once; the raw rows pass 1 also writes
         # are not algorithmic traffic); retain: 1 280 B/frame (PCM in, raw out, raw in, normalised out)
         bytes_per_frame = 1280.0 if retain else 960.0
-        achieved = frames_all / world * bytes_per_frame / (ms_max * 1e-3) / 1e9
-        line = {
-            "metric": METRIC, "value": hours_all / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": 2 * n_steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / (2 * n_steps),
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "baseline_config": "cfg5",
-                       "corpus_hours": hours_all, "frames": frames_all, "passes": 2,
-                       "pass2": ("in-place normalisation of the raw log-mel retained in HBM "
-                                 f"({share_bytes / 1e9:.1f} GB per GPU)") if retain
-                                else "fbank recomputed with the normalisation fused into its epilogue",
-                       "collective": "one all-reduce (SUM) of 161 float64 between the passes",
-                       "global_frames_in_statistics": float(acc[160]),
-                       "l2": f"cycling {R} resident batches per GPU (~{R * 204} MB of PCM + features)",
-                       "parallelism": f"utterance-sharded x{world}"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "note": f"per GPU; {bytes_per_frame:.0f} algorithmic bytes per frame for the two-pass global CMVN"},
-            "clocks": clk, "gpu_launches": 4 * n_steps + len(plans),
-        }
-        print(json.dumps(line), flush=True)
+        res = {"value": hours_all / (ms_max * 1e-3), "ms": ms_max, "hours": hours_all, "frames": frames_all,
+               "retain": retain, "share_bytes": share_bytes, "bytes_per_frame": bytes_per_frame,
+               "achieved": frames_all / world * bytes_per_frame / (ms_max * 1e-3) / 1e9, "n_steps": n_steps,
+               "R": R, "n_plans": len(plans), "clk": clk, "check": check, "allreduce_us": allreduce_us,
+               "ranks_seen": int(ranks_seen), "acc160": float(acc[160]),
+               "allreduce_impl": "C ABI ncclAllReduce" if comm is not None else "torch.distributed"}
     for p in plans:
         p.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    del store
+    return res
+
+
+def sweep_line(args, world, res):
+    peak, peak_src = measured_peaks()
+    retain, n_steps = res["retain"], res["n_steps"]
+    return {
+        "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world,
+        "steps": 2 * n_steps, "warmup": max(args.warmup, 3), "ms_per_step": res["ms"] / (2 * n_steps),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "baseline_config": "cfg5",
+                   "corpus_hours": res["hours"], "frames": res["frames"], "passes": 2,
+                   "pass2": ("in-place normalisation of the raw log-mel retained in HBM "
+                             f"({res['share_bytes'] / 1e9:.1f} GB per GPU)") if retain
+                            else "fbank recomputed with the normalisation fused into its epilogue",
+                   "collective": "one all-reduce (SUM) of 161 float64 between the passes",
+                   "allreduce_impl": res["allreduce_impl"], "allreduce_us": res["allreduce_us"],
+                   "global_frames_in_statistics": res["acc160"], "stats_check": res["check"],
+                   "l2": f"cycling {res['R']} resident batches per GPU (~{res['R'] * 204} MB of PCM + features)",
+                   "parallelism": f"utterance-sharded x{world}"},
+        "roofline": {"bound": "hbm", "achieved": res["achieved"], "peak": peak, "unit": "GB/s",
+                     "frac": res["achieved"] / peak, "traffic": None, "peak_source": peak_src,
+                     "note": f"per GPU; {res['bytes_per_frame']:.0f} algorithmic bytes per frame for the two-pass "
+                             "global CMVN"},
+        "clocks": res["clk"], "gpu_launches": 4 * n_steps + res["n_plans"],
+    }
 
 
 def main():

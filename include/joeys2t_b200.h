@@ -172,6 +172,9 @@ int js2t_nccl_comm_create(const void* id128, int world_size, int rank, int devic
 int js2t_nccl_comm_destroy(void* nccl_comm);
 int js2t_global_stats_finalize(js2t_plan* plan, const double* accum_dev, void* stream);
 int js2t_normalize_execute(js2t_plan* plan, float* out_dev, void* stream);
+/* The plan's global statistics as the kernels use them: mean[80] | 1/std[80] in float32, copied device to
+ * device on `stream` (for checks across ranks: they must be bit-identical everywhere). */
+int js2t_plan_copy_global_stats(const js2t_plan* plan, float* dst_dev, void* stream);
 
 /* ---- PCM ingest: 48 kHz -> 16 kHz -------------------------------------------
  * Replaces scripts/gradio_demo.py:35-45 reformat_freq for sr == 48000:

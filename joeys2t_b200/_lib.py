@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = [
     "js2t_features_execute", "js2t_plan_enable_profiling", "js2t_plan_kernel_times_ms",
     "js2t_plan_set_option", "js2t_plan_debug_times", "js2t_plan_utt_stats", "js2t_plan_copy_utt_stats", "js2t_global_stats_accumulate",
     "js2t_global_stats_allreduce", "js2t_nccl_unique_id", "js2t_nccl_comm_create", "js2t_nccl_comm_destroy",
-    "js2t_global_stats_finalize", "js2t_normalize_execute",
+    "js2t_global_stats_finalize", "js2t_normalize_execute", "js2t_plan_copy_global_stats",
     "js2t_reformat_48k_to_16k",
 ]
 
@@ -54,6 +54,16 @@ def nvcc_command(out: Path = LIB_PATH, extra=()):
         "--shared", "-Xcompiler", "-fPIC", *extra, "-o", str(out), *[str(CSRC / s) for s in SOURCES],
         "-ldl"
     ]
+
+
+def kernel_source_sha16() -> str:
+    """Hash of the device code of the hot path: profiles keyed by it (ncu counters,
+    DRAM traffic) are only attached to a bench line when they belong to the build being measured."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("fbank_kernels.cu", "js2t_internal.h", "mel_structure.inc"):  # device code of the hot path
+        h.update((CSRC / f).resolve().read_bytes())
+    return h.hexdigest()[:16]
 
 
 def is_stale() -> bool:
@@ -120,6 +130,7 @@ def _declare(lib):
     lib.js2t_nccl_comm_destroy.argtypes = [vp]
     lib.js2t_global_stats_finalize.argtypes = [vp, vp, vp]
     lib.js2t_normalize_execute.argtypes = [vp, vp, vp]
+    lib.js2t_plan_copy_global_stats.argtypes = [vp, vp, vp]
     lib.js2t_reformat_48k_to_16k.argtypes = [vp, vp, i32, i64, vp, vp, vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)

@@ -894,6 +894,18 @@ int js2t_global_stats_finalize(js2t_plan* plan, const double* accum_dev, void* s
   return JS2T_OK;
 }
 
+int js2t_plan_copy_global_stats(const js2t_plan* plan, float* dst_dev, void* stream) {
+  if (plan == nullptr || dst_dev == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
+  if (!plan->global_stats_set) return fail(JS2T_ERR_STATE, "no global statistics set");
+  DeviceGuard guard(plan->ctx->device);
+  JS2T_CUDA(guard.err);
+  JS2T_CUDA(plan_begin(const_cast<js2t_plan*>(plan), (cudaStream_t)stream));
+  // d_gmean | d_gistd are adjacent (one carve of 160 floats)
+  JS2T_CUDA(cudaMemcpyAsync(dst_dev, plan->d_gmean, sizeof(float) * 2 * kMel, cudaMemcpyDeviceToDevice,
+                            (cudaStream_t)stream));
+  return JS2T_OK;
+}
+
 int js2t_normalize_execute(js2t_plan* plan, float* out_dev, void* stream_) {
   if (plan == nullptr || out_dev == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
   if (!plan->global_stats_set) return fail(JS2T_ERR_STATE, "no global statistics set");

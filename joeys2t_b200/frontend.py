@@ -275,6 +275,12 @@ class Plan:
     def finalize_global(self, accum: torch.Tensor) -> None:
         _lib.check(self._lib.js2t_global_stats_finalize(self._h, accum.data_ptr(), self._stream()))
 
+    def global_mean_istd(self) -> torch.Tensor:
+        """(160,) float32 on the device: the global mean[80] | 1/std[80] the kernels normalise with."""
+        out = torch.empty(2 * NUM_MEL, dtype=torch.float32, device=f"cuda:{self.ctx.device}")
+        _lib.check(self._lib.js2t_plan_copy_global_stats(self._h, out.data_ptr(), self._stream()))
+        return out
+
     def normalize(self, out: torch.Tensor) -> torch.Tensor:
         _lib.check(self._lib.js2t_normalize_execute(self._h, out.data_ptr(), self._stream()))
         return out

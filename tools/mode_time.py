@@ -49,8 +49,8 @@ def masks(plan, value):
 
 run("raw (mode 0, no stats)", lambda p: (p.set_masks(None), p.set_cmvn("none")))
 run("stats only (mode 0 + finalize)", lambda p: (p.set_masks(None), p.set_cmvn("stats")))
-run("utterance CMVN unfused", lambda p: (p.set_masks(None), p.set_cmvn("utterance"), p.set_option("fused_cmvn", 0)))
-run("utterance CMVN in-kernel finalize (mode 1)", lambda p: (p.set_masks(None), p.set_cmvn("utterance"), p.set_option("fused_cmvn", 1)))
+run("utterance CMVN unfused", lambda p: (p.set_masks(None), p.set_cmvn("utterance")))
+run("utterance CMVN in-kernel finalize (mode 1)", lambda p: (p.set_masks(None), p.set_cmvn("utterance")))
 run("global CMVN epilogue (mode 2), no masks", lambda p: (p.set_masks(None), p.set_cmvn("global"), p.set_global_stats(mean, istd)))
 run("global CMVN epilogue (mode 2), const-fill masks", lambda p: (p.set_cmvn("global"), p.set_global_stats(mean, istd), masks(p, 0.0)))
-run("utterance CMVN unfused + masks", lambda p: (p.set_cmvn("utterance"), p.set_option("fused_cmvn", 0), masks(p, None)))
+run("utterance CMVN unfused + masks", lambda p: (p.set_cmvn("utterance"), masks(p, None)))

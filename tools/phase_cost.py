@@ -25,7 +25,6 @@ frames = np.mean([s[0].total_frames for s in sets])
 def timeit(skip, n=30, fused=False):
     for plan, _, _ in sets:
         plan.set_option("debug_skip", skip)
-        plan.set_option("force_unfused", 0 if fused else 1)
         plan.set_cmvn("utterance" if fused else "stats")
     for i in range(6):
         p, d, o = sets[i % R]
@@ -58,7 +57,6 @@ for skip, name in {64: "no normalisation", 128: "no fence", 192: "no normalisati
     print(f"skip {skip:3d} ({name:28s}): {t:7.1f} us   delta {fb - t:7.1f} us")
 for plan, _, _ in sets:
     plan.set_option("debug_skip", 0)
-    plan.set_option("force_unfused", 1)
     plan.set_cmvn("utterance")
 for i in range(6):
     p, d, o = sets[i % R]

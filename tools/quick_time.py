@@ -25,7 +25,6 @@ def timeit(mode, unfused, n=40, reps=3):
     best = 1e9
     for plan, _, _ in sets:
         plan.set_cmvn(mode)
-        plan.set_option("force_unfused", unfused)
     for _ in range(reps):
         for i in range(8):
             p, d, o = sets[i % R]

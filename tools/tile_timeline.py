@@ -19,7 +19,6 @@ if mode == "global":
     plan.set_global_stats(np.full(80, 5.0), np.full(80, 0.25))
 else:
     plan.set_cmvn(mode)
-plan.set_option("fused_cmvn", 0 if "--unfused" in sys.argv else 1)
 plan.set_option("debug_times", 1)
 dev = packed.to_device()
 out = plan.empty_output()
