@@ -99,6 +99,10 @@ int js2t_plan_create_features(js2t_ctx* ctx, int n_utts, const int32_t* n_frames
                               const int32_t* max_frames, int layout, int pad_tmax, float pad_value,
                               js2t_plan** out);
 int js2t_plan_destroy(js2t_plan* plan);
+/* Same without waiting: the caller guarantees that everything it enqueued with this plan has completed
+ * (for example it waited on an event recorded behind the last execute).  For hosts that retire plans
+ * behind events while newer batches are already in flight on the same stream. */
+int js2t_plan_destroy_completed(js2t_plan* plan);
 
 int64_t js2t_plan_total_frames(const js2t_plan* plan); /* sum of emitted frames */
 int64_t js2t_plan_out_rows(const js2t_plan* plan);     /* rows of 80 floats the output needs */
@@ -119,6 +123,16 @@ int js2t_plan_set_global_stats(js2t_plan* plan, const double* mean80, const doub
  * `mask_value = spectrogram.mean()` (:45-46), CONST uses value_const.  table == NULL clears. */
 int js2t_plan_set_masks(js2t_plan* plan, int n_fmask, int n_tmask, const int32_t* table,
                         int value_mode, float value_const, void* stream);
+
+/* Dither COMPATIBILITY / TEST mode (TA:179-181: strided_input + randn(T, 400) * dither).  The reference's
+ * call site never enables dither (joeynmt/helpers_for_audio.py:34-36 -> 0.0, the default of every other
+ * entry point here); this reproduces torchaudio's behaviour for callers who do, with the noise drawn on the
+ * host so that results are reproducible: noise_dev is float32 (js2t_plan_total_frames(), 400) on the device,
+ * already multiplied by the dither constant, frames of the batch in utterance order; it is added to each
+ * frame's samples (int16-range values) before DC removal.  The pointer is borrowed — it must stay valid
+ * for every later execute; NULL switches the mode off.  Slower than the default path (the two frames a
+ * lane processes no longer share their samples); not on the benchmarked path. */
+int js2t_plan_set_dither(js2t_plan* plan, const float* noise_dev);
 
 /* ---- the hot path ---------------------------------------------------------------------------
  * pcm_dev -> out_dev according to the plan (fbank [-> CMVN] [-> SpecAugment], padded or ragged).
@@ -175,6 +189,15 @@ int js2t_normalize_execute(js2t_plan* plan, float* out_dev, void* stream);
 /* The plan's global statistics as the kernels use them: mean[80] | 1/std[80] in float32, copied device to
  * device on `stream` (for checks across ranks: they must be bit-identical everywhere). */
 int js2t_plan_copy_global_stats(const js2t_plan* plan, float* dst_dev, void* stream);
+
+/* ---- host-side packing ------------------------------------------------------------------------
+ * Gathers the per-utterance waveform arrays of one batch (what the reference's per-item API hands over:
+ * joeynmt/helpers_for_audio.py:41-47 `waveform`, one array per call) into the packed staging buffer the
+ * plan describes: utterance u's n_bytes[u] bytes go to dst + dst_byte_off[u].  Pure host code, spread
+ * over a small persistent pool of threads (n_threads <= 0: the pool's default; 1: the calling thread
+ * only).  dst should be pinned memory so that the following H2D copy is asynchronous. */
+int js2t_pack_pcm(int n_utts, const void* const* src, const int64_t* n_bytes, const int64_t* dst_byte_off,
+                  void* dst, int64_t dst_capacity, int n_threads);
 
 /* ---- PCM ingest: 48 kHz -> 16 kHz -------------------------------------------
  * Replaces scripts/gradio_demo.py:35-45 reformat_freq for sr == 48000:

@@ -28,14 +28,14 @@ MASK_VALUE_MEAN, MASK_VALUE_CONST = 0, 1
 # every symbol include/joeys2t_b200.h declares (tests check the .so exports all of them)
 EXPORTED_SYMBOLS = [
     "js2t_version", "js2t_last_error", "js2t_num_frames", "js2t_ctx_create", "js2t_ctx_destroy",
-    "js2t_ctx_set_tables", "js2t_plan_create", "js2t_plan_create_features", "js2t_plan_destroy",
+    "js2t_ctx_set_tables", "js2t_plan_create", "js2t_plan_create_features", "js2t_plan_destroy", "js2t_plan_destroy_completed",
     "js2t_plan_total_frames", "js2t_plan_out_rows", "js2t_plan_get_frames", "js2t_plan_get_out_rows",
-    "js2t_plan_set_cmvn", "js2t_plan_set_global_stats", "js2t_plan_set_masks", "js2t_fbank_execute",
+    "js2t_plan_set_cmvn", "js2t_plan_set_global_stats", "js2t_plan_set_masks", "js2t_plan_set_dither", "js2t_fbank_execute",
     "js2t_features_execute", "js2t_plan_enable_profiling", "js2t_plan_kernel_times_ms",
     "js2t_plan_set_option", "js2t_plan_debug_times", "js2t_plan_utt_stats", "js2t_plan_copy_utt_stats", "js2t_global_stats_accumulate",
     "js2t_global_stats_allreduce", "js2t_nccl_unique_id", "js2t_nccl_comm_create", "js2t_nccl_comm_destroy",
     "js2t_global_stats_finalize", "js2t_normalize_execute", "js2t_plan_copy_global_stats",
-    "js2t_reformat_48k_to_16k",
+    "js2t_reformat_48k_to_16k", "js2t_pack_pcm",
 ]
 
 
@@ -106,6 +106,7 @@ def _declare(lib):
     lib.js2t_plan_create.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, f32, P(vp)]
     lib.js2t_plan_create_features.argtypes = [vp, i32, vp, vp, i32, i32, f32, P(vp)]
     lib.js2t_plan_destroy.argtypes = [vp]
+    lib.js2t_plan_destroy_completed.argtypes = [vp]
     lib.js2t_plan_total_frames.restype = i64
     lib.js2t_plan_total_frames.argtypes = [vp]
     lib.js2t_plan_out_rows.restype = i64
@@ -115,6 +116,7 @@ def _declare(lib):
     lib.js2t_plan_set_cmvn.argtypes = [vp, i32, i32, i32, i32]
     lib.js2t_plan_set_global_stats.argtypes = [vp, vp, vp, vp]
     lib.js2t_plan_set_masks.argtypes = [vp, i32, i32, vp, i32, f32, vp]
+    lib.js2t_plan_set_dither.argtypes = [vp, vp]
     lib.js2t_fbank_execute.argtypes = [vp, vp, vp, vp]
     lib.js2t_features_execute.argtypes = [vp, vp, vp, vp]
     lib.js2t_plan_enable_profiling.argtypes = [vp, i32]
@@ -132,6 +134,7 @@ def _declare(lib):
     lib.js2t_normalize_execute.argtypes = [vp, vp, vp]
     lib.js2t_plan_copy_global_stats.argtypes = [vp, vp, vp]
     lib.js2t_reformat_48k_to_16k.argtypes = [vp, vp, i32, i64, vp, vp, vp]
+    lib.js2t_pack_pcm.argtypes = [i32, vp, vp, vp, vp, i64, i32]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is c.c_int and name not in ("js2t_version",):

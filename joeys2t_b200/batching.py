@@ -123,7 +123,10 @@ class SpeechBatchCollator:
         kept = [int(i) for i, k in zip(indices, keep) if k]
         if src is None:
             raise ValueError(f"every item of the batch {list(indices)} was filtered out")
-        src_length = torch.tensor(lengths, dtype=torch.long, device=src.device)
+        # pinned + non-blocking: a pageable host-to-device copy would wait for everything enqueued so far
+        # (the batch's own H2D and kernels) and serialise the caller with the GPU
+        host_len = torch.tensor(lengths, dtype=torch.long).pin_memory()
+        src_length = host_len.to(src.device, non_blocking=True)
         return src, src_length, kept
 
 

@@ -9,8 +9,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "js2t_internal.h"
@@ -134,6 +137,8 @@ struct js2t_plan {
   float* d_gistd = nullptr;
   double* d_utt_stats = nullptr;
   int* d_sched = nullptr;    // [2] tile scheduler counters of the persistent kernel (self-resetting)
+  long long* d_frame_row0 = nullptr;  // [n_utts] frames emitted before utterance u (rows of the dither noise array)
+  const float* dither = nullptr;      // compatibility mode: caller-owned noise (total_frames, 400), or NULL
   int max_utt_tiles = 0;
   int* d_masks = nullptr;
   size_t masks_cap = 0;
@@ -401,6 +406,7 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
   const size_t o_g = carve(sizeof(float) * 2 * kMel);
   const size_t o_ustats = carve(sizeof(double) * kStatsPerTile * n_utts);
   const size_t o_sched = carve(sizeof(int) * 2);
+  const size_t o_row0 = carve(sizeof(long long) * n_utts);
   DeviceGuard guard(ctx->device);
   cudaError_t e = guard.err;
   if (e == cudaSuccess) e = pool_alloc(ctx, off, &p->d_ws, &p->ws_cap);
@@ -419,6 +425,15 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
   p->d_gistd = p->d_gmean + kMel;
   p->d_utt_stats = reinterpret_cast<double*>(base + o_ustats);
   p->d_sched = reinterpret_cast<int*>(base + o_sched);
+  p->d_frame_row0 = reinterpret_cast<long long*>(base + o_row0);
+  std::vector<long long> row0(n_utts);
+  {
+    long long acc = 0;
+    for (int u = 0; u < n_utts; ++u) {
+      row0[u] = acc;
+      acc += p->h_utts[u].n_frames;
+    }
+  }
   // Asynchronous upload on the context's own stream.  The sources are pageable: cudaMemcpyAsync returns
   // once they have been staged (so `tiles` may go out of scope), and the DMA itself is ordered on
   // upload_stream in front of ready_ev, which every execute stream waits for (plan_begin).
@@ -429,6 +444,8 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
     e = cudaMemcpyAsync(p->d_utts, p->h_utts.data(), sizeof(UttDesc) * n_utts, cudaMemcpyHostToDevice, us);
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(p->d_tiles, tiles.data(), sizeof(TileDesc) * tiles.size(), cudaMemcpyHostToDevice, us);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(p->d_frame_row0, row0.data(), sizeof(long long) * n_utts, cudaMemcpyHostToDevice, us);
   if (e == cudaSuccess) e = cudaEventRecord(p->ready_ev, us);
   if (e != cudaSuccess) {
     cudaStreamSynchronize(us);
@@ -455,13 +472,15 @@ int js2t_plan_create_features(js2t_ctx* ctx, int n_utts, const int32_t* n_frames
                             pad_value, out);
 }
 
-int js2t_plan_destroy(js2t_plan* plan) {
+static int plan_destroy_impl(js2t_plan* plan, bool wait) {
   if (plan == nullptr) return JS2T_OK;
   DeviceGuard guard(plan->ctx->device);
   for (cudaEvent_t e : plan->prof_ev) cudaEventDestroy(e);
   // like the cudaFree it replaces, destroying a plan waits for whatever still uses its workspace —
-  // but only for that (an event behind the plan's latest launch), not for the whole device
-  plan_quiesce(plan);
+  // but only for the streams the plan was used on, not for the whole device; a caller that already
+  // knows the plan's work has completed (js2t_plan_destroy_completed) skips even that
+  if (wait) plan_quiesce(plan);
+  else if (plan->ready_ev) cudaEventSynchronize(plan->ready_ev);
   if (plan->ready_ev) cudaEventDestroy(plan->ready_ev);
   if (plan->d_masks) pool_free(plan->ctx, plan->d_masks, plan->masks_cap);
   if (plan->d_dbg) cudaFree(plan->d_dbg);
@@ -469,6 +488,9 @@ int js2t_plan_destroy(js2t_plan* plan) {
   delete plan;
   return JS2T_OK;
 }
+
+int js2t_plan_destroy(js2t_plan* plan) { return plan_destroy_impl(plan, /*wait=*/true); }
+int js2t_plan_destroy_completed(js2t_plan* plan) { return plan_destroy_impl(plan, /*wait=*/false); }
 
 int64_t js2t_plan_total_frames(const js2t_plan* plan) { return plan ? plan->total_frames : -1; }
 int64_t js2t_plan_out_rows(const js2t_plan* plan) { return plan ? plan->out_rows : -1; }
@@ -547,6 +569,14 @@ int js2t_plan_set_masks(js2t_plan* plan, int n_fmask, int n_tmask, const int32_t
   plan->mask_value_mode = value_mode;
   plan->mask_value_const = value_const;
   plan->has_masks = true;
+  return JS2T_OK;
+}
+
+int js2t_plan_set_dither(js2t_plan* plan, const float* noise_dev) {
+  if (plan == nullptr) return fail(JS2T_ERR_INVALID, "NULL plan");
+  if (plan->feature_input && noise_dev != nullptr)
+    return fail(JS2T_ERR_STATE, "dither applies to PCM plans (js2t_plan_create) only");
+  plan->dither = noise_dev;
   return JS2T_OK;
 }
 
@@ -633,6 +663,8 @@ static int run_pipeline(js2t_plan* plan, const void* in_dev, float* out_dev, cud
   f.pad_tmax = plan->pad_tmax;
   f.pad_value = plan->pad_value;
   f.epilogue = kEpiRaw;
+  f.dither = from_pcm ? plan->dither : nullptr;
+  f.dither_row0 = plan->d_frame_row0;
   f.dbg_skip = plan->dbg_skip;
   f.grid_limit = plan->grid_limit;
   f.dbg_times = plan->d_dbg;
@@ -658,7 +690,7 @@ static int run_pipeline(js2t_plan* plan, const void* in_dev, float* out_dev, cud
   // (2) global CMVN with known statistics and no data-dependent fill value: normalise (+ mask) in
   //     the fbank epilogue, still one pass
   const bool mean_fill = masks && plan->mask_value_mode == JS2T_MASK_VALUE_MEAN;
-  if (from_pcm && mode == JS2T_CMVN_GLOBAL && !mean_fill && plan->before &&
+  if (from_pcm && mode == JS2T_CMVN_GLOBAL && !mean_fill && plan->before && plan->dither == nullptr &&
       (!masks || plan->n_fmask + plan->n_tmask <= 16)) {
     f.epilogue = kEpiNormKnown;
     f.g_mean = plan->d_gmean;
@@ -928,6 +960,129 @@ int js2t_normalize_execute(js2t_plan* plan, float* out_dev, void* stream_) {
   if (e == cudaSuccess) e = launch_apply(a, stream);
   plan->cmvn_mode = saved;
   JS2T_CUDA(e);
+  return JS2T_OK;
+}
+
+// ---- host-side packing of a ragged batch into one (pinned) staging buffer ------------------------
+// The per-batch callers of the reference API hand over one array per utterance (pageable memory); the
+// device path wants them back to back, 16-byte aligned, in pinned memory.  A single-threaded copy of a
+// 20 000-frame batch (6.4 MB) costs more than its H2D transfer, so the copy is spread over a small
+// persistent pool of worker threads (chunks of 256 KB, claimed with an atomic counter).
+namespace {
+
+class CopyPool {
+ public:
+  struct Chunk {
+    const char* src;
+    char* dst;
+    size_t n;
+  };
+  explicit CopyPool(int n_workers) {
+    for (int i = 0; i < n_workers; ++i) workers_.emplace_back([this] { loop(); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  int size() const { return (int)workers_.size(); }
+  // copies all chunks; the calling thread works too; returns when everything is done
+  void run(const std::vector<Chunk>& chunks, int n_helpers) {
+    std::lock_guard<std::mutex> serial(run_mu_);  // one batch at a time per pool
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      chunks_ = &chunks;
+      next_.store(0);
+      done_.store(0);
+      wanted_ = std::min(n_helpers, (int)workers_.size());
+      ++epoch_;
+    }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [&] { return done_.load() == chunks.size() && active_ == 0; });
+    chunks_ = nullptr;
+  }
+
+ private:
+  void work() {
+    const std::vector<Chunk>& c = *chunks_;
+    for (;;) {
+      const size_t i = next_.fetch_add(1);
+      if (i >= c.size()) break;
+      memcpy(c[i].dst, c[i].src, c[i].n);
+      done_.fetch_add(1);
+    }
+  }
+  void loop() {
+    unsigned long long seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || (epoch_ != seen && chunks_ != nullptr && wanted_ > 0); });
+        if (stop_) return;
+        seen = epoch_;
+        --wanted_;
+        ++active_;
+      }
+      work();
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        --active_;
+      }
+      done_cv_.notify_all();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_, run_mu_;
+  std::condition_variable cv_, done_cv_;
+  const std::vector<Chunk>* chunks_ = nullptr;
+  std::atomic<size_t> next_{0}, done_{0};
+  unsigned long long epoch_ = 0;
+  int wanted_ = 0, active_ = 0;
+  bool stop_ = false;
+};
+
+CopyPool* copy_pool() {
+  static CopyPool* pool = [] {
+    unsigned hw = std::thread::hardware_concurrency();
+    int n = hw > 2 ? (int)std::min(hw / 2, 8u) - 1 : 0;  // + the calling thread
+    return new CopyPool(n < 0 ? 0 : n);
+  }();
+  return pool;
+}
+
+}  // namespace
+
+int js2t_pack_pcm(int n_utts, const void* const* src, const int64_t* n_bytes, const int64_t* dst_byte_off,
+                  void* dst, int64_t dst_capacity, int n_threads) {
+  if (n_utts < 0 || (n_utts > 0 && (src == nullptr || n_bytes == nullptr || dst_byte_off == nullptr || dst == nullptr)))
+    return fail(JS2T_ERR_INVALID, "js2t_pack_pcm: NULL argument");
+  constexpr size_t kChunk = 256 * 1024;
+  std::vector<CopyPool::Chunk> chunks;
+  size_t total = 0;
+  for (int u = 0; u < n_utts; ++u) {
+    if (n_bytes[u] < 0 || dst_byte_off[u] < 0 || dst_byte_off[u] + n_bytes[u] > dst_capacity)
+      return fail(JS2T_ERR_INVALID, "js2t_pack_pcm: utterance %d (%lld bytes at %lld) does not fit in %lld bytes", u,
+                  (long long)n_bytes[u], (long long)dst_byte_off[u], (long long)dst_capacity);
+    if (n_bytes[u] > 0 && src[u] == nullptr) return fail(JS2T_ERR_INVALID, "js2t_pack_pcm: src[%d] is NULL", u);
+    for (size_t o = 0; o < (size_t)n_bytes[u]; o += kChunk)
+      chunks.push_back({static_cast<const char*>(src[u]) + o, static_cast<char*>(dst) + dst_byte_off[u] + o,
+                        std::min(kChunk, (size_t)n_bytes[u] - o)});
+    total += (size_t)n_bytes[u];
+  }
+  if (chunks.empty()) return JS2T_OK;
+  CopyPool* pool = copy_pool();
+  int helpers = n_threads > 0 ? n_threads - 1 : pool->size();
+  if (total < 4 * kChunk) helpers = 0;  // small batches: waking the workers costs more than the copy
+  if (helpers <= 0) {
+    for (const auto& c : chunks) memcpy(c.dst, c.src, c.n);
+    return JS2T_OK;
+  }
+  pool->run(chunks, helpers);
   return JS2T_OK;
 }
 

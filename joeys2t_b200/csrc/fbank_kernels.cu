@@ -507,7 +507,11 @@ __device__ __forceinline__ double sum_tile_column(const float* ts, int n) {
 constexpr int kModeRaw = 0, kModeNormKnown = 2;
 constexpr int kMaxEpilogueMasks = 16;
 
-template <int kMode>
+// kDither: compatibility / test mode only (kaldi.py:179-181, never enabled by the reference's call site):
+// host-drawn noise (sum T, 400) is added to every frame's samples before DC removal.  The two frames of a
+// pair then no longer share their samples, so this variant keeps one set of d values per frame; it is
+// slower and not on the benchmarked path.
+template <int kMode, bool kDither = false>
 __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaunch p) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* sWin = reinterpret_cast<float*>(smem + kOffWin);
@@ -672,9 +676,57 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
           //   (x_j - m) - 0.97 (x_{j-1} - m) = d_j - 0.03 m, and window[0] = 0 exactly kills the
           //   replicate-padded first sample (kaldi.py:193-198), so d does not depend on the frame.
           float de[18], dO[18];  // d of the even / odd sample of the pair
+          float deB[kDither ? 13 : 1], dOB[kDither ? 13 : 1];  // dither: frame lA + 1 has its own
           float sa = 0.f, sb = 0.f, mid = 0.f;
           const unsigned char* slot0 = sRaw + (kslot & 1u) * kSlotBytes;
-          if (!f32) {
+          if constexpr (kDither) {
+            // x + noise per frame (kaldi.py:179-181: strided_input + randn * dither, float32), then the
+            // same d = x[j] - 0.97 x[j-1] and sums, separately for the two frames of the pair.  Noise rows
+            // are indexed by the frame's position in the (sum T, 400) array; a past-the-end partner frame
+            // (odd frame count) reuses the last valid row — its results land in unused columns of P.
+            const long long row_a = p.dither_row0[cur.utt] + cur.frame0 + lA;
+            const long long row_b = row_a + ((lA + 1 < nf) ? 1 : 0);
+            const float* nzA = p.dither + row_a * kFrameLen;
+            const float* nzB = p.dither + row_b * kFrameLen;
+            const unsigned char* sl = (f32 && fA >= 16) ? sRaw + ((kslot + 1u) & 1u) * kSlotBytes : slot0;
+            const unsigned* rw = (split && half)
+                                     ? reinterpret_cast<const unsigned*>(slot0 + 16 + kSplitOff) + 80 * (lA - 16) + r
+                                     : reinterpret_cast<const unsigned*>(slot0 + 16) + 80 * lA + r;
+            const float* rf = reinterpret_cast<const float*>(sl + 16) + kHop * (lA & 15) + 2 * r;
+#pragma unroll
+            for (int n = 0; n < 18; ++n) {
+              float x0, x1, xm;
+              if (!f32) {
+                const unsigned wc = rw[16 * n], wp = rw[16 * n - 1];
+                x0 = (float)(short)(wc & 0xffffu);
+                x1 = (float)(short)(wc >> 16);
+                xm = (float)(short)(wp >> 16);
+              } else {
+                const bool in = (n < 17) || (r < 8);  // row 17, lanes >= 8: beyond the staged samples
+                x0 = in ? rf[32 * n] * 32768.f : 0.f;
+                x1 = in ? rf[32 * n + 1] * 32768.f : 0.f;
+                xm = in ? rf[32 * n - 1] * 32768.f : 0.f;
+              }
+              if (n <= 12) {
+                const int j = 32 * n + 2 * r;
+                const bool in = j < kFrameLen;
+                const float a0 = in ? x0 + nzA[j] : 0.f, a1 = in ? x1 + nzA[j + 1] : 0.f;
+                const float am = (in && j > 0) ? xm + nzA[j - 1] : a0;  // j == 0: replicate pad (window[0] == 0)
+                de[n] = fmaf(-kPreemph, am, a0);
+                dO[n] = fmaf(-kPreemph, a0, a1);
+                sa += a0 + a1;
+              }
+              if (n >= 5) {
+                const int j = 32 * (n - 5) + 2 * r;
+                const bool in = j < kFrameLen;
+                const float b0 = in ? x0 + nzB[j] : 0.f, b1 = in ? x1 + nzB[j + 1] : 0.f;
+                const float bm = (in && j > 0) ? xm + nzB[j - 1] : b0;
+                deB[n - 5] = fmaf(-kPreemph, bm, b0);
+                dOB[n - 5] = fmaf(-kPreemph, b0, b1);
+                sb += b0 + b1;
+              }
+            }
+          } else if (!f32) {
             const unsigned* rw = (split && half)
                                      ? reinterpret_cast<const unsigned*>(slot0 + 16 + kSplitOff) + 80 * (lA - 16) + r
                                      : reinterpret_cast<const unsigned*>(slot0 + 16) + 80 * lA + r;
@@ -721,8 +773,10 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
               else if (r < 8) sb += sx;
             }
           }
-          sa += mid;
-          sb += mid;
+          if constexpr (!kDither) {
+            sa += mid;
+            sb += mid;
+          }
           // per-frame DC mean (kaldi.py:183-186), reduced over the half-warp and pre-multiplied by
           // (1 - 0.97)
           u64 mc;
@@ -747,8 +801,8 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
 #pragma unroll
           for (int n1 = 0; n1 < 13; ++n1) {
             const float2 w = *reinterpret_cast<const float2*>(wfr + 32 * n1);
-            v[n1].re = mul2(sub2(pk(de[n1], de[n1 + 5]), mc), bc(w.x));
-            v[n1].im = mul2(sub2(pk(dO[n1], dO[n1 + 5]), mc), bc(w.y));
+            v[n1].re = mul2(sub2(pk(de[n1], kDither ? deB[n1] : de[n1 + 5]), mc), bc(w.x));
+            v[n1].im = mul2(sub2(pk(dO[n1], kDither ? dOB[n1] : dO[n1 + 5]), mc), bc(w.y));
           }
           // row 12: lanes r >= 8 are past sample 399 of the frame (window = 0); what they read may lie
           // beyond the staged samples and, for float PCM, need not be finite
@@ -1330,6 +1384,7 @@ int fbank_persistent_grid() {
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(fbank_tile_kernel<kModeRaw>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     cudaFuncSetAttribute(fbank_tile_kernel<kModeNormKnown>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(fbank_tile_kernel<kModeRaw, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fbank_tile_kernel<kModeRaw>, kThreads, kSmemBytes);
     if (occ < 1) occ = 1;
     g_fbank_grid = occ * n_sm;  // every CTA resident at once: one wave, persistent
@@ -1359,6 +1414,10 @@ cudaError_t launch_fbank(const FbankLaunch& p, cudaStream_t s) {
   int full = fbank_persistent_grid();
   if (p.grid_limit > 0 && p.grid_limit < full) full = p.grid_limit;  // tuning only (option "max_ctas")
   const int grid = p.n_tiles < full ? p.n_tiles : full;
+  if (p.dither != nullptr) {  // compatibility mode: raw epilogue only (capi.cu routes CMVN through the apply kernel)
+    if (p.epilogue != kEpiRaw) return cudaErrorInvalidValue;
+    return launch_pdl(fbank_tile_kernel<kModeRaw, true>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
+  }
   if (p.epilogue == kEpiNormKnown)
     return launch_pdl(fbank_tile_kernel<kModeNormKnown>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
   return launch_pdl(fbank_tile_kernel<kModeRaw>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);

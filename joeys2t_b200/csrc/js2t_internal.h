@@ -73,6 +73,10 @@ struct FbankLaunch {
   const int* masks;     // [n_utts][n_masks][2] (start, width); first n_fmask are frequency masks
   int n_fmask, n_tmask;
   const float* mask_value;  // [n_utts]
+  // dither compatibility mode (kaldi.py:179-181): noise[(sum T)][400] added to the frames before DC removal;
+  // dither_row0[u] = first row of utterance u in that array.  nullptr = off (the reference's dither = 0).
+  const float* dither;
+  const long long* dither_row0;
   int grid_limit;  // tuning only: cap on the persistent grid (0 = all resident CTAs)
   int dbg_skip;  // tuning only: bit0 staging, bit1 FFT phase, bit2 mel, bit3 store, bit4 butterflies, bit5 exchange
   unsigned long long* dbg_times;  // [n_tiles][4] globaltimer stamps (debug / tuning only) or nullptr

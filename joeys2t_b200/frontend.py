@@ -129,9 +129,13 @@ class PackedPCM:
         else:
             pin = torch.cuda.is_available()
             self.host = torch.empty(max(self.nbytes, 16), dtype=torch.uint8, pin_memory=pin)
-        hv = self.host.numpy()
-        for a, o in zip(arrs, self.byte_off):
-            hv[o:o + a.nbytes] = a.view(np.uint8)
+        # gather on the C side (js2t_pack_pcm: a persistent pool of copy threads) — the numpy slice loop it
+        # replaces was a third of a per-batch call
+        n = len(arrs)
+        ptrs = (ctypes.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        _lib.check(_lib.load().js2t_pack_pcm(n, ptrs, sizes.ctypes.data, self.byte_off.ctypes.data,
+                                             self.host.data_ptr(), self.host.numel(), 0))
+        self._keep = arrs  # the sources stay alive until the copy above has returned (it has)
 
     def to_device(self, device=None, non_blocking: bool = True) -> torch.Tensor:
         return self.host.to(device or "cuda", non_blocking=non_blocking)
@@ -219,6 +223,20 @@ class Plan:
                                                  self._stream()))
         return self
 
+    def set_dither(self, noise: Optional[torch.Tensor]) -> "Plan":
+        """Compatibility / test mode (torchaudio ``fbank(dither=d)``, kaldi.py:179-181): ``noise`` is the
+        host-drawn ``randn(total_frames, 400) * d`` as a float32 CUDA tensor, added to the frames before DC
+        removal.  ``None`` switches it off (the reference's call site never enables dither)."""
+        if noise is None:
+            self._dither = None
+            _lib.check(self._lib.js2t_plan_set_dither(self._h, None))
+            return self
+        assert noise.is_cuda and noise.dtype == torch.float32 and noise.is_contiguous()
+        assert tuple(noise.shape) == (self.total_frames, tables.FRAME_LENGTH), noise.shape
+        self._dither = noise  # borrowed by the C side: keep it alive
+        _lib.check(self._lib.js2t_plan_set_dither(self._h, noise.data_ptr()))
+        return self
+
     # ---- execution --------------------------------------------------------------------------
     def empty_output(self) -> torch.Tensor:
         shape = (self.n_utts, self.pad_tmax, NUM_MEL) if self.layout == "padded" else \
@@ -290,9 +308,11 @@ class Plan:
         flat = out.reshape(-1, NUM_MEL)
         return [flat[r:r + t] for r, t in zip(self.out_row.tolist(), self.n_frames.tolist())]
 
-    def close(self):
+    def close(self, completed: bool = False):
+        """Destroy the plan.  ``completed=True``: the caller has already waited for the plan's last work
+        (an event), so nothing is synchronised — newer batches on the same stream keep running."""
         if self._h:
-            self._lib.js2t_plan_destroy(self._h)
+            (self._lib.js2t_plan_destroy_completed if completed else self._lib.js2t_plan_destroy)(self._h)
             self._h = ctypes.c_void_p()
 
     def __del__(self):
@@ -306,17 +326,58 @@ class Plan:
 # one-call batched entry point
 # ------------------------------------------------------------------------------------------
 _tls = threading.local()
+_RING = 4          # pinned staging buffers per calling thread
+_MAX_PENDING = 8   # plans whose work may still be in flight before the oldest is waited for
 
 
-def _staging(nbytes: int) -> torch.Tensor:
-    """Grow-only pinned staging buffer of the calling thread.  The one-call entry points below
-    synchronise before they return, so the buffer is free again by the next call; allocating pinned
-    memory per call cost more than the kernels for a single utterance."""
-    buf = getattr(_tls, "staging", None)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, pin_memory=True)
-        _tls.staging = buf
-    return buf
+class _Staging:
+    """Per-thread ring of grow-only pinned staging buffers.  The one-call entry points below return as
+    soon as their work is ENQUEUED (the output tensor is ordered on the caller's stream like any torch
+    result): a slot is reused only after the H2D copy that read it has completed (an event per slot), and
+    a plan is destroyed only after the kernels that use its workspace have (``pending``).  Allocating
+    pinned memory, creating / destroying a plan and synchronising per call used to cost 60x the kernels
+    of a 20 000-frame batch."""
+
+    def __init__(self):
+        self.bufs = [None] * _RING
+        self.events = [None] * _RING
+        self.next = 0
+        self.pending = []  # (event, plan, device tensors to keep alive)
+
+    def acquire(self, nbytes: int) -> Tuple[int, torch.Tensor]:
+        j = self.next
+        self.next = (j + 1) % _RING
+        if self.events[j] is not None:
+            self.events[j].synchronize()  # normally long complete
+        buf = self.bufs[j]
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, pin_memory=True)
+            self.bufs[j] = buf
+        return j, buf
+
+    def release_after(self, j: int, stream: torch.cuda.Stream) -> None:
+        ev = self.events[j] or torch.cuda.Event()
+        ev.record(stream)
+        self.events[j] = ev
+
+    def retire(self, plan: "Plan", keep, stream: torch.cuda.Stream) -> None:
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        self.pending.append((ev, plan, keep))
+        self.reap(limit=_MAX_PENDING)
+
+    def reap(self, limit: int = 0) -> None:
+        while self.pending and (len(self.pending) > limit or self.pending[0][0].query()):
+            ev, plan, _ = self.pending.pop(0)
+            ev.synchronize()
+            plan.close(completed=True)
+
+
+def _staging_state() -> _Staging:
+    st = getattr(_tls, "state", None)
+    if st is None:
+        st = _tls.state = _Staging()
+    return st
 
 
 def fbank_cmvn_specaug_ragged(
@@ -331,6 +392,7 @@ def fbank_cmvn_specaug_ragged(
     layout: str = "ragged",
     pad_value: float = 1.0,
     global_stats: Optional[Tuple[np.ndarray, np.ndarray]] = None,
+    dither_noise: Optional[Array] = None,
 ) -> Tuple[torch.Tensor, np.ndarray]:
     """Whole batch in one call: pack → H2D → fbank [→ CMVN] [→ SpecAugment] on the GPU.
 
@@ -340,10 +402,21 @@ def fbank_cmvn_specaug_ragged(
         ``None`` = raw log-mel
     :param masks: int32 (B, n_fmask + n_tmask, 2) host-drawn SpecAugment table (see
         :func:`joeys2t_b200.data_augmentation.draw_masks`)
+    :param dither_noise: compatibility / test mode — host-drawn ``randn(sum T, 400) * dither`` (float32),
+        see :meth:`Plan.set_dither`; ``None`` = the reference's ``dither = 0``
     :returns: (features on the GPU — ragged ``(sum T, 80)`` or padded ``(B, Tmax, 80)`` —, n_frames)
     """
     _require_cuda()
-    packed = PackedPCM(waveforms, host=_staging)
+    st = _staging_state()
+    st.reap()
+    slot = []
+
+    def take(nbytes):
+        j, buf = st.acquire(nbytes)
+        slot.append(j)
+        return buf
+
+    packed = PackedPCM(waveforms, host=take)
     plan = Plan(packed.n_samples, packed.byte_off, packed.is_f32, max_frames=max_frames,
                 layout=layout, pad_value=pad_value)
     if global_stats is not None:
@@ -356,12 +429,19 @@ def fbank_cmvn_specaug_ragged(
                       cmvn.get("before", True))
     if masks is not None:
         plan.set_masks(masks, n_fmask, n_tmask, mask_value)
+    noise_dev = None
+    if dither_noise is not None:
+        noise_dev = torch.as_tensor(dither_noise, dtype=torch.float32).contiguous().to(
+            f"cuda:{plan.ctx.device}")
+        plan.set_dither(noise_dev)
+    stream = torch.cuda.current_stream(plan.ctx.device)
     dev_pcm = packed.host[:max(packed.nbytes, 16)].to(f"cuda:{plan.ctx.device}", non_blocking=True)
+    st.release_after(slot[0], stream)   # the staging slot is free again once the H2D copy has read it
     out = plan.execute(dev_pcm)
     n_frames = plan.n_frames.copy()
-    # the plan's workspace and the staging buffer must outlive the enqueued copies and kernels
-    torch.cuda.current_stream().synchronize()
-    plan.close()
+    # asynchronous return: the plan's workspace and the device PCM outlive the enqueued kernels (retired
+    # behind an event on this stream); `out` is ordered on the current stream like any torch result
+    st.retire(plan, (dev_pcm, noise_dev), stream)
     return out, n_frames
 
 

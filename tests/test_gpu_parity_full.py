@@ -258,3 +258,46 @@ def test_get_torchaudio_fbank_takes_int16_range_floats(fe, fixtures_pcm, ref_fba
         assert np.array_equal(got, direct)
     with pytest.raises(ValueError):
         _get_torchaudio_fbank(torch.zeros(1, 1000), 8000)
+
+
+# ------------------------------------------------------------------------------------------------
+# dither compatibility mode (kaldi.py:179-181; the reference's call site leaves dither at 0)
+# ------------------------------------------------------------------------------------------------
+def test_dither_compat_mode_vs_torchaudio(fe, fixtures_pcm):
+    """north_star: "Dither ... come[s] from the host so results are reproducible".  torchaudio draws
+    randn(T, 400) per utterance and adds randn * dither to the frames before DC removal; the same noise, drawn
+    on the host under the same seed, goes through js2t_plan_set_dither: int16 and float32 PCM, an odd frame
+    count (a partner frame past the end), one utterance that spans several tiles."""
+    ta_kaldi = pytest.importorskip("torchaudio.compliance.kaldi")
+    pcm, _ = fixtures_pcm
+    waves = [pcm[0], pcm[3].astype(np.float32) / np.float32(32768.0), pcm[6], pcm[1][:400 + 160 * 2], pcm[2]]
+    dither = 1.0
+    refs, noises = [], []
+    for i, w in enumerate(waves):
+        x = torch.from_numpy(w.astype(np.float32) if w.dtype == np.int16 else w * np.float32(32768.0))[None]
+        torch.manual_seed(100 + i)
+        refs.append(ta_kaldi.fbank(x, num_mel_bins=80, sample_frequency=16000, dither=dither).numpy())
+        torch.manual_seed(100 + i)
+        noises.append((torch.randn(refs[-1].shape[0], 400) * dither).numpy())
+    noise = np.concatenate(noises, 0)
+    out, nf = fe.fbank_cmvn_specaug_ragged(waves, dither_noise=noise)
+    got = out.cpu().numpy()
+    assert nf.tolist() == [r.shape[0] for r in refs]
+    plain, _ = fe.fbank_cmvn_specaug_ragged(waves)
+    plain = plain.cpu().numpy()
+    off = 0
+    for u, ref in enumerate(refs):
+        t = ref.shape[0]
+        assert np.abs(got[off:off + t] - ref).max() <= LOGMEL_ATOL, u
+        assert np.abs(plain[off:off + t] - ref).max() > 1e-2, u  # the noise really went in
+        off += t
+    # with utterance CMVN on top (three-kernel path) and in the padded layout
+    outc, _ = fe.fbank_cmvn_specaug_ragged(waves, cmvn={}, dither_noise=noise, layout="padded")
+    outc = outc.cpu().numpy()
+    for u, ref in enumerate(refs):
+        if ref.shape[0] >= 100:  # CMVN over the 3-frame utterance divides by near-zero stds: ill-conditioned
+            assert_cmvn_close(outc[u, :ref.shape[0]], O.cmvn(ref), f"utterance {u}")
+        assert (outc[u, ref.shape[0]:] == 1.0).all()
+    # zero noise == dither off, bit for bit
+    zero, _ = fe.fbank_cmvn_specaug_ragged(waves, dither_noise=np.zeros_like(noise))
+    assert np.array_equal(zero.cpu().numpy(), plain)

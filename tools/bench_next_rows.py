@@ -89,16 +89,50 @@ np.random.seed(1)
 for b in batches[:2]:
     collate(b)
 torch.cuda.synchronize()
+for b in batches:  # every staging slot and pool buffer has been allocated once
+    collate(b)
+torch.cuda.synchronize()
 t0 = time.perf_counter()
 audio = 0.0
-for b in batches:
-    src, ln, _ = collate(b)
-    audio += sum(len(waves[i]) for i in b) / 16000
+for rep in range(3):
+    for b in batches:
+        src, ln, _ = collate(b)
+        audio += sum(len(waves[i]) for i in b) / 16000
 torch.cuda.synchronize()
-dt = time.perf_counter() - t0
+dt = (time.perf_counter() - t0)
+batches_timed = 3 * len(batches)
+# host-side gather alone (js2t_pack_pcm, pinned destination): pool of copy threads vs one thread
+import ctypes  # noqa: E402
+from joeys2t_b200 import _lib  # noqa: E402
+b0 = batches[0]
+arrs = [waves[i] for i in b0]
+sizes = np.array([a.nbytes for a in arrs], np.int64)
+offs = np.concatenate([[0], np.cumsum((sizes + 15) // 16 * 16)[:-1]]).astype(np.int64)
+dstbuf = torch.empty(int(offs[-1] + sizes[-1] + 16), dtype=torch.uint8, pin_memory=True)
+ptrs = (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+pack_us = {}
+for thr in (1, 0):
+    for _ in range(5):
+        _lib.load().js2t_pack_pcm(len(arrs), ptrs, sizes.ctypes.data, offs.ctypes.data, dstbuf.data_ptr(), dstbuf.numel(), thr)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        _lib.load().js2t_pack_pcm(len(arrs), ptrs, sizes.ctypes.data, offs.ctypes.data, dstbuf.data_ptr(), dstbuf.numel(), thr)
+    pack_us[thr] = (time.perf_counter() - t0) / 50 * 1e6
+print(f"js2t_pack_pcm of one batch ({sizes.sum() / 1e6:.1f} MB into pinned memory): {pack_us[1]:.0f} us on one thread, "
+      f"{pack_us[0]:.0f} us with the copy pool")
 print(f"token batches of 20000 frames (librispeech_100h.yaml:83-85): {len(batches)} batches from 256 utterances; "
-      f"sampler {t_sampler * 1e3:.2f} ms total (no audio touched); collate {dt / len(batches) * 1e3:.2f} ms per batch wall "
+      f"sampler {t_sampler * 1e3:.2f} ms total (no audio touched); collate {dt / batches_timed * 1e3:.2f} ms per batch wall "
       f"= {audio / 3600 / dt:7.1f} audio-h/s through the per-batch Python path (pack + H2D + 3 kernels)")
+
+import cProfile  # noqa: E402
+import pstats  # noqa: E402
+pr = cProfile.Profile()
+pr.enable()
+for b in batches:
+    collate(b)
+torch.cuda.synchronize()
+pr.disable()
+pstats.Stats(pr).sort_stats("tottime").print_stats(14)
 
 # ---- f-3 ------------------------------------------------------------------------------------------
 print("\n## f-3  extract_corpus: 256 utterances (0.89 audio-h) -> fbank80.zip (npy-in-ZIP_STORED) on tmpfs")
