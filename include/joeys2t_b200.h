@@ -81,6 +81,11 @@ int js2t_ctx_destroy(js2t_ctx* ctx);
  * row-major, TA:436-511).  The bank must have the two-adjacent-filters-per-bin structure of the
  * reference configuration, otherwise JS2T_ERR_TABLES.  Must be called once before any execute. */
 int js2t_ctx_set_tables(js2t_ctx* ctx, const float* window400, const float* mel80x256);
+/* The bank the kernels were compiled with (80 x 256 floats, row-major): torchaudio's
+ * get_mel_banks(80, 512, 16000, 20, 0) (TA:436-511), bit for bit.  For hosts whose own float32 `log`
+ * rounds differently from the build machine's: they can compare their bank against this one and decide,
+ * instead of being locked out by js2t_ctx_set_tables' bit-exact check. */
+int js2t_reference_mel_bank(float* mel80x256_out);
 
 /* ---- plan: one ragged batch ------------------------------------------------------------------
  * n_utts utterances packed in one PCM buffer.  pcm_byte_off[u] (multiple of 16) is where utterance

@@ -28,7 +28,7 @@ MASK_VALUE_MEAN, MASK_VALUE_CONST = 0, 1
 # every symbol include/joeys2t_b200.h declares (tests check the .so exports all of them)
 EXPORTED_SYMBOLS = [
     "js2t_version", "js2t_last_error", "js2t_num_frames", "js2t_ctx_create", "js2t_ctx_destroy",
-    "js2t_ctx_set_tables", "js2t_plan_create", "js2t_plan_create_features", "js2t_plan_destroy", "js2t_plan_destroy_completed",
+    "js2t_ctx_set_tables", "js2t_reference_mel_bank", "js2t_plan_create", "js2t_plan_create_features", "js2t_plan_destroy", "js2t_plan_destroy_completed",
     "js2t_plan_total_frames", "js2t_plan_out_rows", "js2t_plan_get_frames", "js2t_plan_get_out_rows",
     "js2t_plan_set_cmvn", "js2t_plan_set_global_stats", "js2t_plan_set_masks", "js2t_plan_set_dither", "js2t_fbank_execute",
     "js2t_features_execute", "js2t_plan_enable_profiling", "js2t_plan_kernel_times_ms",
@@ -103,6 +103,7 @@ def _declare(lib):
     lib.js2t_ctx_create.argtypes = [i32, P(vp)]
     lib.js2t_ctx_destroy.argtypes = [vp]
     lib.js2t_ctx_set_tables.argtypes = [vp, vp, vp]
+    lib.js2t_reference_mel_bank.argtypes = [vp]
     lib.js2t_plan_create.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, f32, P(vp)]
     lib.js2t_plan_create_features.argtypes = [vp, i32, vp, vp, i32, i32, f32, P(vp)]
     lib.js2t_plan_destroy.argtypes = [vp]

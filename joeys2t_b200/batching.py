@@ -92,10 +92,20 @@ class FrameCountBatchSampler:
         if len(batch) > 0 and not self.drop_last:
             yield batch
 
+    @property
+    def num_samples(self) -> int:
+        """``len(sampler)`` — UNFILTERED, like the reference's ``SentenceBatchSampler.num_samples``
+        (datasets.py:1180-1192): schedulers and epoch-length computations built on ``len(batch_sampler)``
+        must see the same number with either sampler."""
+        try:
+            return len(self.sampler)
+        except (NotImplementedError, TypeError):
+            return len(self.n_frames)
+
     def __len__(self) -> int:
         if self.batch_type == "token":
             raise NotImplementedError  # like TokenBatchSampler.__len__ (datasets.py:1294-1295)
-        n = sum(self.src_length(int(i)) is not None for i in self.sampler)
+        n = self.num_samples  # datasets.py:1213-1218: items the filters will drop are counted too
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 
 

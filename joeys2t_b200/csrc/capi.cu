@@ -3,6 +3,9 @@
 #include "../../include/joeys2t_b200.h"
 
 #include <dlfcn.h>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -228,6 +231,19 @@ int js2t_ctx_destroy(js2t_ctx* ctx) {
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   for (auto& b : ctx->pool) cudaFree(b.second);
   delete ctx;
+  return JS2T_OK;
+}
+
+int js2t_reference_mel_bank(float* mel80x256_out) {
+  if (mel80x256_out == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
+  float wu[256], wd[256];
+  reference_mel_weights(wu, wd);
+  memset(mel80x256_out, 0, sizeof(float) * 80 * 256);
+  for (int s = 0; s < JS2T_MEL_NUM_SEGMENTS; ++s)
+    for (int k = kMelSegLo[s]; k <= kMelSegHi[s]; ++k) {
+      if (s < 80) mel80x256_out[s * 256 + k] = wu[k];
+      if (s >= 1) mel80x256_out[(s - 1) * 256 + k] = wd[k];
+    }
   return JS2T_OK;
 }
 
@@ -970,6 +986,35 @@ int js2t_normalize_execute(js2t_plan* plan, float* out_dev, void* stream_) {
 // persistent pool of worker threads (chunks of 256 KB, claimed with an atomic counter).
 namespace {
 
+// Copy into the staging buffer with NON-TEMPORAL stores.  The destination is pinned memory that only the
+// GPU's DMA engine reads next: with ordinary stores the lines stay dirty in the caches of whichever cores
+// ran the copy threads, and the H2D transfer that follows has to snoop them out one by one — measured on
+// the B200 host: 6 GB/s instead of 51 GB/s for the copy after a pooled memcpy (profiles/r2h_*).
+void stream_copy(char* dst, const char* src, size_t n) {
+#if defined(__x86_64__)
+  size_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+  if (head > n) head = n;
+  if (head) memcpy(dst, src, head);
+  size_t i = head;
+  for (; i + 64 <= n; i += 64) {
+    const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+    const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 16));
+    const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 32));
+    const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 48));
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), a);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 16), b);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 32), c);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 48), d);
+  }
+  for (; i + 16 <= n; i += 16)
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i)));
+  if (i < n) memcpy(dst + i, src + i, n - i);
+  _mm_sfence();
+#else
+  memcpy(dst, src, n);
+#endif
+}
+
 class CopyPool {
  public:
   struct Chunk {
@@ -1013,7 +1058,7 @@ class CopyPool {
     for (;;) {
       const size_t i = next_.fetch_add(1);
       if (i >= c.size()) break;
-      memcpy(c[i].dst, c[i].src, c[i].n);
+      stream_copy(c[i].dst, c[i].src, c[i].n);
       done_.fetch_add(1);
     }
   }
@@ -1079,7 +1124,7 @@ int js2t_pack_pcm(int n_utts, const void* const* src, const int64_t* n_bytes, co
   int helpers = n_threads > 0 ? n_threads - 1 : pool->size();
   if (total < 4 * kChunk) helpers = 0;  // small batches: waking the workers costs more than the copy
   if (helpers <= 0) {
-    for (const auto& c : chunks) memcpy(c.dst, c.src, c.n);
+    for (const auto& c : chunks) stream_copy(c.dst, c.src, c.n);
     return JS2T_OK;
   }
   pool->run(chunks, helpers);

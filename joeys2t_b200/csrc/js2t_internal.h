@@ -119,6 +119,7 @@ struct ApplyLaunch {
 };
 
 cudaError_t upload_mel_weights(const float* wu256, const float* wd256, cudaStream_t s);
+void reference_mel_weights(float* wu256, float* wd256);  // the compiled-in two-band weights
 int check_mel_weights(const float* wu256, const float* wd256);  // first bin that differs from the compiled-in weights, or -1
 cudaError_t launch_fbank(const FbankLaunch& p, cudaStream_t s);
 cudaError_t launch_features(const FbankLaunch& p, cudaStream_t s);  // p.pcm = feature rows

@@ -37,21 +37,31 @@ def draw_masks(num_frames: int, num_freqs: int, freq_mask_n: int, freq_mask_f: i
         no-ops whose draws were still consumed, like the reference — or ``None`` when the reference
         returns its input untouched (no frames, or fewer frequency bins than ``freq_mask_f``).
     """
+    rows = _draw_mask_rows(num_frames, num_freqs, freq_mask_n, freq_mask_f, time_mask_n, time_mask_t,
+                           time_mask_p)
+    return None if rows is None else np.array(rows, np.int32)
+
+
+def _draw_mask_rows(num_frames, num_freqs, freq_mask_n, freq_mask_f, time_mask_n, time_mask_t, time_mask_p):
+    """The draws themselves, as a list of (start, width) tuples (one numpy array per BATCH is built by
+    :func:`mask_tables_for_batch`; per-row array writes were most of the per-batch host time)."""
     if num_frames == 0 or num_freqs < freq_mask_f:  # :48-52
         return None
-    table = np.zeros((freq_mask_n + time_mask_n, 2), np.int32)
-    for i in range(freq_mask_n):  # :54-58
-        f = np.random.randint(0, freq_mask_f)
-        f0 = np.random.randint(0, num_freqs - f)
-        table[i] = (f0, f)
+    randint = np.random.randint
+    rows = []
+    for _ in range(freq_mask_n):  # :54-58
+        f = int(randint(0, freq_mask_f))
+        f0 = int(randint(0, num_freqs - f))
+        rows.append((f0, f))
     max_time_mask_t = min(time_mask_t, math.floor(num_frames * time_mask_p))  # :60-62
     if max_time_mask_t < 1:  # :63-64 frequency masks only
-        return table
-    for i in range(time_mask_n):  # :66-70
-        t = np.random.randint(0, max_time_mask_t)
-        t0 = np.random.randint(0, num_frames - t)
-        table[freq_mask_n + i] = (t0, t)
-    return table
+        rows.extend([(0, 0)] * time_mask_n)
+        return rows
+    for _ in range(time_mask_n):  # :66-70
+        t = int(randint(0, max_time_mask_t))
+        t0 = int(randint(0, num_frames - t))
+        rows.append((t0, t))
+    return rows
 
 
 class SpecAugment:
@@ -138,10 +148,13 @@ def mask_tables_for_batch(specaugment: "SpecAugment", n_frames,
     """Draw the SpecAugment tables of a whole batch in utterance order (= the order in which the
     reference's per-item loop would consume the RNG).  Utterances the reference leaves untouched
     get all-zero-width rows."""
-    n_masks = specaugment.freq_mask_n + specaugment.time_mask_n
-    table = np.zeros((len(n_frames), n_masks, 2), np.int32)
-    for u, t in enumerate(n_frames):
-        tb = specaugment.draw(int(t), num_freqs)
-        if tb is not None:
-            table[u] = tb
-    return table, specaugment.freq_mask_n, specaugment.time_mask_n
+    sa = specaugment
+    n_masks = sa.freq_mask_n + sa.time_mask_n
+    empty = [(0, 0)] * n_masks
+    rows = []
+    for t in n_frames:
+        r = _draw_mask_rows(int(t), num_freqs, sa.freq_mask_n, sa.freq_mask_f, sa.time_mask_n,
+                            sa.time_mask_t, sa.time_mask_p)
+        rows.append(empty if r is None else r)
+    table = np.array(rows, np.int32).reshape(len(rows), n_masks, 2)
+    return table, sa.freq_mask_n, sa.time_mask_n

@@ -26,37 +26,57 @@ import numpy as np
 from joeys2t_b200.helpers_for_audio import _is_npy_data
 
 
+def _member_payload_span(archive, info: zipfile.ZipInfo) -> Tuple[int, int]:
+    """(offset, size) of a STORED member's payload, from its LOCAL file header: 30 fixed bytes, then the
+    name and the extra field whose lengths are the two little-endian uint16 at bytes 26-29.  The reference
+    assumes ``header_offset + 30 + len(filename)`` (``audiodata_utils.py:52``), i.e. an empty extra field;
+    that is what ``create_zip`` and :class:`ZipFeatureWriter` write, and it is asserted here."""
+    archive.seek(info.header_offset)
+    fixed = archive.read(30)
+    if len(fixed) != 30 or fixed[:4] != b"PK\x03\x04":
+        raise ValueError(f"{info.filename}: no local file header at byte {info.header_offset}")
+    name_len = int.from_bytes(fixed[26:28], "little")
+    extra_len = int.from_bytes(fixed[28:30], "little")
+    if info.compress_type != zipfile.ZIP_STORED or extra_len != 0:
+        raise ValueError(f"{info.filename}: the manifest format addresses uncompressed members without extra field")
+    return info.header_offset + 30 + name_len, info.file_size
+
+
 def get_zip_manifest(zip_path: Path, npy_root: Optional[Path] = None) -> Dict[str, str]:
-    """``audiodata_utils.py:45-63`` — ``{utt_id: "<zip name>:<offset>:<size>"}`` for every member."""
-    manifest = {}
-    with zipfile.ZipFile(zip_path, mode="r") as f:
-        info = f.infolist()
-    # retrieve offsets
-    with zip_path.open("rb") as f:
-        for i in info:
-            utt_id = Path(i.filename).stem
-            offset, file_size = i.header_offset + 30 + len(i.filename), i.file_size
-            f.seek(offset)
-            data = f.read(file_size)
-            assert len(data) > 1 and _is_npy_data(data), (utt_id, len(data))
-            manifest[utt_id] = f"{zip_path.name}:{offset}:{file_size}"
-            # sanity check
+    """Interface of ``scripts/audiodata_utils.py:45-63``: ``{utt_id: "<zip name>:<offset>:<size>"}`` for
+    every member of an uncompressed archive — the strings ``get_features`` resolves
+    (``joeynmt/helpers_for_audio.py:77-89``).  With ``npy_root`` every member is additionally compared with
+    ``<npy_root>/<utt_id>.npy``."""
+    zip_path = Path(zip_path)
+    with zipfile.ZipFile(zip_path) as zf:
+        members = [m for m in zf.infolist() if not m.is_dir()]
+    manifest: Dict[str, str] = {}
+    with open(zip_path, "rb") as archive:
+        for member in members:
+            utt_id = Path(member.filename).stem
+            offset, size = _member_payload_span(archive, member)
+            archive.seek(offset)
+            payload = archive.read(size)
+            if len(payload) != size or not _is_npy_data(payload):
+                raise AssertionError(f"{zip_path.name}: member {member.filename} is not a .npy image")
             if npy_root is not None:
-                byte_data = np.load(io.BytesIO(data))
-                npy_data = np.load((npy_root / f"{utt_id}.npy").as_posix())
-                assert np.allclose(byte_data, npy_data)
+                on_disk = np.load(str(Path(npy_root) / f"{utt_id}.npy"))
+                if not np.allclose(np.load(io.BytesIO(payload)), on_disk):
+                    raise AssertionError(f"{utt_id}: archive member differs from {npy_root}/{utt_id}.npy")
+            manifest[utt_id] = f"{zip_path.name}:{offset}:{size}"
     return manifest
 
 
 def create_zip(data_root: Path, zip_path: Path) -> None:
-    """``audiodata_utils.py:66-73`` — pack every ``*.npy`` of ``data_root`` uncompressed."""
-    paths = list(data_root.glob("*.npy"))
-    with zipfile.ZipFile(zip_path, "w", zipfile.ZIP_STORED) as f:
-        for path in paths:
-            try:
-                f.write(path, arcname=path.name)
-            except Exception as e:  # pylint: disable=broad-except
-                raise RuntimeError(f"{path}") from e
+    """Interface of ``scripts/audiodata_utils.py:66-73``: every ``*.npy`` of ``data_root`` into one
+    uncompressed archive.  The payloads are copied as they are (no re-serialisation), through the same
+    writer as the batched path, so the manifest of the result is known without re-reading it."""
+    with ZipFeatureWriter(Path(zip_path)) as writer:
+        for path in sorted(Path(data_root).glob("*.npy")):
+            payload = path.read_bytes()
+            if not _is_npy_data(payload):
+                raise RuntimeError(f"{path}: not a .npy file")
+            writer.add_npy_image(path.stem, payload)
 
 
 def save_tsv(df, path: Path, header: bool = True) -> None:
@@ -95,10 +115,15 @@ class ZipFeatureWriter:
 
     def add(self, utt_id: str, features: np.ndarray) -> str:
         assert features.ndim == 2, "spectrogram must be a 2-D array."
+        entry = self.add_npy_image(utt_id, npy_bytes(features))
+        self.n_frames[utt_id] = int(features.shape[0])
+        return entry
+
+    def add_npy_image(self, utt_id: str, data: bytes) -> str:
+        """Append an already serialised ``.npy`` image as member ``<utt_id>.npy``."""
         if utt_id in self.manifest:
             raise ValueError(f"duplicate utterance id {utt_id!r}")
         name = f"{utt_id}.npy"
-        data = npy_bytes(features)
         info = zipfile.ZipInfo(name)  # fixed timestamp: archives are reproducible
         info.compress_type = zipfile.ZIP_STORED
         self._zf.writestr(info, data)
@@ -107,7 +132,6 @@ class ZipFeatureWriter:
         offset = written.header_offset + 30 + len(name.encode("utf-8")) + len(written.extra)
         entry = f"{self.zip_path.name}:{offset}:{len(data)}"
         self.manifest[utt_id] = entry
-        self.n_frames[utt_id] = int(features.shape[0])
         return entry
 
     def close(self) -> Dict[str, str]:

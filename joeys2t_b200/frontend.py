@@ -46,6 +46,19 @@ class Context:
         _lib.check(lib.js2t_ctx_create(device, ctypes.byref(self._h)))
         win = np.ascontiguousarray(tables.povey_window(), np.float32)
         mel = np.ascontiguousarray(tables.mel_banks(NUM_MEL), np.float32)
+        # The mel weights are compile-time immediates and js2t_ctx_set_tables checks the uploaded bank bit for
+        # bit.  `mel` comes from this host's float32 log(): if it rounds differently from the build machine's
+        # (a last-place difference), upload the compiled-in bank instead of locking the host out — but only
+        # for last-place differences; a bank that is really different (rate, bin count, low_freq) still fails.
+        ref = np.zeros_like(mel)
+        _lib.check(lib.js2t_reference_mel_bank(ref.ctypes.data))
+        if not np.array_equal(mel, ref):
+            ulp = np.abs(mel.view(np.int32).astype(np.int64) - ref.view(np.int32).astype(np.int64))
+            if ((mel == 0) == (ref == 0)).all() and int(ulp.max()) <= 2:
+                import warnings
+                warnings.warn(f"joeys2t_b200: this host's mel bank differs from the compiled-in one by {int(ulp.max())} "
+                              f"ulp in {int((ulp > 0).sum())} weights (float32 log rounding); using the compiled-in bank")
+                mel = ref
         _lib.check(lib.js2t_ctx_set_tables(self._h, win.ctypes.data, mel.ctypes.data))
 
     @property

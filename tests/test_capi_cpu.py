@@ -111,3 +111,42 @@ def test_packed_pcm_into_caller_staging():
     assert asked == [own.nbytes]
     with pytest.raises(ValueError):
         frontend.PackedPCM(waves, host=torch.zeros(own.nbytes - 1, dtype=torch.uint8))
+
+
+def test_reference_mel_bank_is_torchaudios(ref_tables):
+    """js2t_reference_mel_bank: the bank the kernels were compiled with == torchaudio's get_mel_banks output
+    (tests/golden/ref_tables.npz), bit for bit.  Pure host code."""
+    lib = _lib.load()
+    bank = np.zeros((80, 256), np.float32)
+    assert lib.js2t_reference_mel_bank(bank.ctypes.data) == _lib.OK
+    assert np.array_equal(bank.view(np.uint32), ref_tables["mel80x256"].view(np.uint32))
+
+
+def test_pack_pcm_gathers_ragged_batches():
+    """js2t_pack_pcm (host only): every utterance lands at its 16-byte aligned offset, for one thread and for
+    the copy pool, int16 and float32 mixed, unaligned sources."""
+    import ctypes
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    for trial in range(6):
+        arrs = []
+        for _ in range(int(rng.integers(1, 24))):
+            n = int(rng.integers(1, 300000))
+            a = rng.integers(-30000, 30000, n + 3).astype(np.int16)[int(rng.integers(0, 3)):][:n]
+            arrs.append(np.ascontiguousarray(a) if rng.uniform() < 0.5 else
+                        np.ascontiguousarray(a.astype(np.float32) / np.float32(32768.0)))
+        sizes = np.array([a.nbytes for a in arrs], np.int64)
+        off = np.concatenate([[0], np.cumsum((sizes + 15) // 16 * 16)[:-1]]).astype(np.int64)
+        total = int(off[-1] + sizes[-1])
+        dst = np.full(total + 32, 0xAB, np.uint8)
+        ptrs = (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        rc = lib.js2t_pack_pcm(len(arrs), ptrs, sizes.ctypes.data, off.ctypes.data, dst.ctypes.data, total,
+                               1 if trial % 2 else 0)
+        assert rc == _lib.OK, lib.js2t_last_error()
+        for a, o in zip(arrs, off):
+            assert np.array_equal(dst[o:o + a.nbytes], a.view(np.uint8))
+        assert (dst[total:] == 0xAB).all()
+    # a destination that is too small is refused
+    small = np.zeros(8, np.uint8)
+    rc = lib.js2t_pack_pcm(len(arrs), ptrs, sizes.ctypes.data, off.ctypes.data, small.ctypes.data, 8, 1)
+    assert rc == _lib.ERR_INVALID

@@ -67,13 +67,31 @@ def test_install_swaps_every_symbol_and_restores_cleanly(reference_modules):
     from joeys2t_b200.speech_processor import SpeechProcessor
     jha, jda, jtk = joeys2t_b200.install()
     try:
-        for name in ("extract_fbank_features", "_get_torchaudio_fbank", "get_features", "pad_features"):
+        for name in ("get_features", "pad_features"):
             assert getattr(jha, name) is getattr(ha, name)
+        for name in ("extract_fbank_features", "_get_torchaudio_fbank"):
+            routed = getattr(jha, name)
+            # the shipped geometry (16 kHz, 80 bins) goes to the B200 function; anything else keeps the
+            # reference's own behaviour through the reference's original function
+            assert routed.__wrapped_b200__ is getattr(ha, name)
+            assert routed.__reference_original__ is reference_modules["joeynmt.helpers_for_audio"][name]
+            assert _params(routed) == _params(routed.__reference_original__)
         assert jda.CMVN is da.CMVN and jda.SpecAugment is da.SpecAugment
         assert jtk.CMVN is da.CMVN and jtk.SpecAugment is da.SpecAugment
         assert jtk.SpeechProcessor is SpeechProcessor and jtk.get_features is ha.get_features
         # the reference's own builder now hands out the B200 processor (tokenizers.py:611-619)
         assert sys.modules["joeynmt.tokenizers"].SpeechProcessor is SpeechProcessor
+        # 8 kHz audio (frame geometry 200 / 80 / 256) is outside the B200 path: the call must end up in
+        # the reference's CPU implementation and return what the unpatched reference returns
+        import torch
+        torch.manual_seed(0)
+        wave8k = torch.rand(1, 4000) * 2 - 1
+        with pytest.warns(UserWarning, match="outside the B200 path"):
+            got = jha.extract_fbank_features(wave8k, 8000)
+        want = reference_modules["joeynmt.helpers_for_audio"]["extract_fbank_features"](wave8k, 8000)
+        assert got.shape == want.shape == (1 + (4000 - 200) // 80, 80) and (got == want).all()
+        with pytest.warns(UserWarning):
+            assert jha.extract_fbank_features(torch.rand(1, 8000), 16000, n_mel_bins=40).shape[1] == 40
     finally:
         for modname, mod in (("joeynmt.helpers_for_audio", jha), ("joeynmt.data_augmentation", jda),
                              ("joeynmt.tokenizers", jtk)):
