@@ -70,12 +70,13 @@ constexpr int kCols = 512;  // D: up to 4 independent accumulators of N columns 
 constexpr int kAccs = 4;    // independent accumulator tiles the throughput loop rotates over (a DFT stage has 16)
 
 template <bool kTF32, int N, bool kTS>
-__global__ void __launch_bounds__(128, 1) probe(int n_mma, long long* cycles, int* errors) {
+__global__ void __launch_bounds__(128, 1) probe(int n_mma, int n_issuers, long long* cycles, int* errors) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* sA = smem;                    // 128 rows x 128 bytes
   unsigned char* sB = smem + 128 * kKBytes;    // N rows x 128 bytes
   __shared__ unsigned s_taddr;
   __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ __align__(8) unsigned long long s_bar2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int kEl = kTF32 ? 4 : 2;                  // bytes per element
   constexpr int kK = kKBytes / kEl;                   // K elements of the stage (32 tf32 / 64 bf16)
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(128, 1) probe(int n_mma, long long* cycles, in
   for (int i = tid; i < N * kK; i += 128) put(sB, i / kK, i % kK, b_val(i / kK, i % kK));
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar2)), "r"(n_issuers));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -155,21 +157,22 @@ __global__ void __launch_bounds__(128, 1) probe(int n_mma, long long* cycles, in
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
-  // ---- throughput: n_mma instructions back to back (chains of kSteps), then one commit ---------------
-  long long t0 = 0;
-  if (tid == 0) {
-    t0 = clock64();
-    for (int i = 0, acc = 0; i < n_mma; i += kSteps, acc = (acc + 1) % kAccs) {
-      const unsigned d = tD + (unsigned)(acc * N);  // independent accumulation chains, like the 16 GEMMs of a stage
+  // ---- throughput: n_mma instructions back to back (chains of kSteps) from n_issuers threads (lane 0 of
+  // warps 0..n_issuers-1, each rotating over its own accumulator tiles), one commit per issuer ------------
+  long long t0 = clock64();
+  if (lane == 0 && warp < n_issuers) {
+    const int accs = kAccs / n_issuers > 0 ? kAccs / n_issuers : 1;
+    for (int i = 0, acc = 0; i < n_mma / n_issuers; i += kSteps, acc = (acc + 1) % accs) {
+      const unsigned d = tD + (unsigned)(((warp * accs + acc) % kAccs) * N);
 #pragma unroll
       for (int s = 0; s < kSteps; ++s) {
         if (kTS) mma_ts<kTF32>(d, tA + 8 * s, dB + (uint64_t)((2 * kLBO * s) >> 4), idesc, s > 0);
         else mma_ss<kTF32>(d, dA + (uint64_t)((2 * kLBO * s) >> 4), dB + (uint64_t)((2 * kLBO * s) >> 4), idesc, s > 0);
       }
     }
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar)) : "memory");
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar2)) : "memory");
   }
-  mbar_wait(&s_bar, 1);
+  mbar_wait(&s_bar2, 0);
   if (tid == 0 && blockIdx.x == 0) *cycles = clock64() - t0;
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
@@ -177,13 +180,13 @@ __global__ void __launch_bounds__(128, 1) probe(int n_mma, long long* cycles, in
 }
 
 template <bool kTF32, int N, bool kTS>
-double run(const char* name, long long* cyc, int* err, int n_sm) {
+double run(const char* name, long long* cyc, int* err, int n_sm, int n_issuers = 1) {
   const int n_mma = 4096;
   const int smem = 128 * kKBytes + N * kKBytes;
   cudaFuncSetAttribute(probe<kTF32, N, kTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaMemset(err, 0, 4);
   for (int rep = 0; rep < 2; ++rep) {
-    probe<kTF32, N, kTS><<<n_sm, 128, smem>>>(n_mma, cyc, err);
+    probe<kTF32, N, kTS><<<n_sm, 128, smem>>>(n_mma, n_issuers, cyc, err);
     if (cudaDeviceSynchronize() != cudaSuccess) break;
   }
   long long h = 0;
@@ -192,7 +195,7 @@ double run(const char* name, long long* cyc, int* err, int n_sm) {
   cudaMemcpy(&e, err, sizeof(e), cudaMemcpyDeviceToHost);
   const double per = (double)h / n_mma;
   const double flop = 2.0 * 128 * N * (kTF32 ? 8 : 16);
-  printf("%-34s %7.2f cycles per tcgen05.mma (M=128, N=%d, K=%d)  = %6.0f flop/clk/SM   result errors %d   %s\n", name, per, N,
+  printf("%-34s %d issuer(s) %7.2f cycles per tcgen05.mma (M=128, N=%d, K=%d)  = %6.0f flop/clk/SM   result errors %d   %s\n", name, n_issuers, per, N,
          kTF32 ? 8 : 16, flop / per, e, cudaGetErrorString(cudaGetLastError()));
   return per;
 }
@@ -214,6 +217,15 @@ int main() {
   const double bf_ts = run<false, 32, true>("bf16  N=32  A in tensor memory", cyc, err, n_sm);
   run<false, 64, false>("bf16  N=64  A in shared memory", cyc, err, n_sm);
   run<false, 64, true>("bf16  N=64  A in tensor memory", cyc, err, n_sm);
+  // is the ~45-cycle cost per instruction the issuing thread or the tensor pipe?  several issuing threads:
+  const double tf_ss2 = run<true, 32, false>("tf32  N=32  A in shared memory", cyc, err, n_sm, 2);
+  const double tf_ss4 = run<true, 32, false>("tf32  N=32  A in shared memory", cyc, err, n_sm, 4);
+  const double bf_ss4 = run<false, 32, false>("bf16  N=32  A in shared memory", cyc, err, n_sm, 4);
+  run<false, 64, true>("bf16  N=64  A in tensor memory", cyc, err, n_sm, 4);
+  const double tf_ts4 = run<true, 32, true>("tf32  N=32  A in tensor memory", cyc, err, n_sm, 4);
+  const double bf_ts4 = run<false, 32, true>("bf16  N=32  A in tensor memory", cyc, err, n_sm, 4);
+  run<true, 64, true>("tf32  N=64  A in tensor memory", cyc, err, n_sm, 4);
+  run<true, 32, true>("tf32  N=32  A in tensor memory", cyc, err, n_sm, 2);
   // two stages x 16 GEMMs x (32 K-values per GEMM) per 128-frame tile:
   //   tf32: 4 K-steps per GEMM; products needed for 1e-3 parity (tools/sim_tc_dft.py): 4 (hi/lo x hi/lo)
   //   bf16: 2 K-steps per GEMM; products needed: 6 (three-way split)
@@ -225,5 +237,9 @@ int main() {
   printf("#   tf32 x 4 products: SS %.1f M, TS %.1f M      tf32 x 3 products (fails parity: 1.75e-3): SS %.1f M, TS %.1f M\n",
          fps(tf_ss, 4, 4) / 1e6, fps(tf_ts, 4, 4) / 1e6, fps(tf_ss, 4, 3) / 1e6, fps(tf_ts, 4, 3) / 1e6);
   printf("#   bf16 x 6 products: SS %.1f M, TS %.1f M\n", fps(bf_ss, 2, 6) / 1e6, fps(bf_ts, 2, 6) / 1e6);
+  printf("#   with 2 / 4 issuing threads, A in shared memory: tf32 x 4 products %.1f M / %.1f M, bf16 x 6 products (4 issuers) %.1f M\n",
+         fps(tf_ss2, 4, 4) / 1e6, fps(tf_ss4, 4, 4) / 1e6, fps(bf_ss4, 2, 6) / 1e6);
+  printf("#   with 4 issuing threads, A in tensor memory (best case): tf32 x 4 products %.1f M, bf16 x 6 products %.1f M\n",
+         fps(tf_ts4, 4, 4) / 1e6, fps(bf_ts4, 2, 6) / 1e6);
   return 0;
 }

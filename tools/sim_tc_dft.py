@@ -10,6 +10,7 @@ with the W256 twiddles folded in), with SPLIT-PRECISION operands and fp32 accumu
 
     f16x2   operands as hi + lo fp16 pairs (3 MMAs per product: hi*hi + hi*lo + lo*hi), kind::f16
     tf32x3  the same with tf32 operands (10-bit mantissa, truncated like the hardware does), kind::tf32
+    tf32x3rn  hi rounded to nearest first (cvt.rna), lo = exact remainder (truncated by the MMA)
     f16     single fp16 operands (1 MMA) — what "just use the tensor cores" would give
     bf16x3  three bf16 terms per operand (6 MMAs)
 
@@ -51,6 +52,11 @@ def split(x, mode):
         return [hi, lo]
     if mode == "tf32x3":
         hi = trunc_tf32(x)
+        lo = trunc_tf32(x - hi)
+        return [hi, lo]
+    if mode == "tf32x3rn":  # hi rounded to nearest (cvt.rna.tf32.f32), lo = x - hi exact, truncated by the MMA
+        u = x.view(np.uint32).astype(np.uint64)
+        hi = ((u + 0x1000) & 0xFFFFE000).astype(np.uint32).view(F32)
         lo = trunc_tf32(x - hi)
         return [hi, lo]
     if mode == "bf16x3":
@@ -156,7 +162,8 @@ def main():
     b1, b2 = stage_matrices()
     print("max |log-mel - reference golden| per fixture clip (gate: 1e-3)")
     print(f"{'mode':22s} " + " ".join(f"clip{i:<6d}" for i in range(10)) + "   worst")
-    for mode, order in (("f32", 0), ("f16x2", 1), ("f16x2", 2), ("tf32x3", 1), ("tf32x3", 2), ("bf16x3", 2),
+    for mode, order in (("f32", 0), ("f16x2", 1), ("f16x2", 2), ("tf32x3", 1), ("tf32x3", 2), ("tf32x3rn", 1),
+                        ("tf32x3rn", 2), ("bf16x3", 2),
                         ("f16", 0)):
         errs = []
         for i in range(10):
