@@ -574,7 +574,8 @@ def run_b200(args):
             line["e2e"] = {"value": e2e_hours_all / (e2e_ms_max * 1e-3), "unit": UNIT,
                            "h2d_bytes_per_step": e2e[2], "d2h_bytes_per_step": e2e[3],
                            "gbs_per_direction_per_gpu": max(e2e[2], e2e[3]) * args.steps / (e2e_ms_max * 1e-3) / 1e9,
-                           "host_ceiling_gbs": host_ceiling(),
+                           "gbs_per_direction_all_gpus": max(e2e[2], e2e[3]) * args.steps * world / (e2e_ms_max * 1e-3) / 1e9,
+                           "host_ceiling_gbs": host_ceiling(world),
                            "host_thread_bound_to_gpu_numa_node": bool(numa_bound)}
         if cfg5 is not None:
             line["cfg5"] = cfg5
@@ -613,12 +614,18 @@ def fp32_roofline(metrics, metrics_src, frames_launch, kernel_ms, sm_mhz, n_sm):
     return out
 
 
-def host_ceiling():
-    """Aggregate pinned-memory copy bandwidth of this box measured by tools/h2d_probe.py (committed under
-    profiles/): what bounds the host-resident (e2e) path as GPUs are added."""
+def host_ceiling(n_gpus):
+    """Raw pinned-memory copy ceiling of the 8 x B200 box for ``n_gpus`` GPUs copying at once, both directions
+    concurrently (tools/h2d_probe.py, committed as profiles/h2d_probe.json; GB/s per direction, summed over
+    the GPUs): what bounds the host-resident (e2e) path as GPUs are added — the host side of the box, not the
+    kernels and not one GPU's PCIe link."""
     p = ROOT / "profiles" / "h2d_probe.json"
     try:
-        return json.loads(p.read_text())
+        rows = json.loads(p.read_text())["rows"]
+        row = max((r for r in rows if r["gpus"] <= n_gpus), key=lambda r: r["gpus"])
+        return {"gpus": row["gpus"], "h2d_gbs": row["both:h2d_gbs"], "d2h_gbs": row["both:d2h_gbs"],
+                "h2d_alone_gbs": row["h2d:h2d_gbs"], "d2h_alone_gbs": row["d2h:d2h_gbs"],
+                "source": "profiles/h2d_probe.json (tools/h2d_probe.py on the 8 x B200 box, H2D and D2H concurrently)"}
     except Exception:  # pylint: disable=broad-except
         return None
 
