@@ -53,6 +53,9 @@ __constant__ float c_mel_wd[256];
 static const float h_mel_wu[256] = {JS2T_MEL_WU_VALUES};
 static const float h_mel_wd[256] = {JS2T_MEL_WD_VALUES};
 
+#ifndef JS2T_MIN_CTAS
+#define JS2T_MIN_CTAS 2  // resident CTAs per SM the register allocation is sized for (128 registers per thread)
+#endif
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr float kPreemph = 0.97f;
@@ -107,7 +110,11 @@ constexpr int kOffWin = 0;
 constexpr int kOffTw256 = kOffWin + (kFrameLen + 16) * 4;
 constexpr int kOffTw512 = kOffTw256 + 256 * 8;
 constexpr int kOffExch = kOffTw512 + 136 * 8;
+#if defined(JS2T_PROBE_ALIAS) && JS2T_PROBE_ALIAS
+constexpr int kOffP = kOffExch;  // TIMING PROBE ONLY (wrong results): P on top of the exchange buffers
+#else
 constexpr int kOffP = kOffExch + kWarps * kExchPerWarp * 8;
+#endif
 constexpr int kOffRaw = (kOffP + kPFloats * 4 + 15) / 16 * 16;  // two PCM slots (TMA targets)
 constexpr int kOffBar = kOffRaw + 2 * kSlotBytes;
 constexpr int kSmemBytes = kOffBar + 16;
@@ -116,7 +123,7 @@ static_assert(kWarps * kStatsPerTile * 4 <= kPFloats * 4, "per-warp statistics a
 static_assert(kOffExch % 16 == 0 && kOffP % 16 == 0 && kOffTw256 % 16 == 0 && kOffWin % 16 == 0 &&
                   kOffRaw % 16 == 0 && kOffBar % 8 == 0,
               "alignment");
-static_assert(2 * (kSmemBytes + 1024) <= 227 * 1024, "two CTAs per SM");
+static_assert(JS2T_MIN_CTAS * (kSmemBytes + 1024) <= 227 * 1024, "resident CTAs per SM");
 
 int fbank_smem_bytes() { return kSmemBytes; }
 
@@ -472,6 +479,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 #else
 #define JS2T_WSTAMP(slot)
 #endif
+// TIMING PROBES ONLY (-DJS2T_PROBE_NOBAR=mask, wrong results): drop block barriers inside a tile
+#ifndef JS2T_PROBE_NOBAR
+#define JS2T_PROBE_NOBAR 0
+#endif
+#define JS2T_MIDBAR(bit)                      \
+  do {                                        \
+    if (!(JS2T_PROBE_NOBAR & (bit))) __syncthreads(); \
+  } while (0)
 #define JS2T_STAMP(slot)                                                                     \
   if (p.dbg_times != nullptr && tid == 0) p.dbg_times[(long long)tile * 4 + (slot)] = globaltimer_ns();
 
@@ -512,7 +527,7 @@ constexpr int kMaxEpilogueMasks = 16;
 // pair then no longer share their samples, so this variant keeps one set of d values per frame; it is
 // slower and not on the benchmarked path.
 template <int kMode, bool kDither = false>
-__global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaunch p) {
+__global__ void __launch_bounds__(kThreads, JS2T_MIN_CTAS) fbank_tile_kernel(const FbankLaunch p) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* sWin = reinterpret_cast<float*>(smem + kOffWin);
   float2* sTw256 = reinterpret_cast<float2*>(smem + kOffTw256);
@@ -876,7 +891,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
         }
       }
       JS2T_WSTAMP(3)
-      __syncthreads();
+      JS2T_MIDBAR(1);
       // this tile's PCM slots are free again
       if (is_sched && next_tma && !next_early) prefetch_tile(p, nxt, sRaw, sBar, kslot + cur_slots);
 
@@ -925,7 +940,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
         }
       }
       JS2T_WSTAMP(4)
-      __syncthreads();
+      JS2T_MIDBAR(2);
 
       // ---- phase 4: store.  Warp w owns rows 4w..4w+3; lane owns columns lane, lane+32, lane+64 -------
       {
@@ -992,7 +1007,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_tile_kernel(const FbankLaun
             st[lane] = s0; st[lane + 32] = s1;
             st[kMel + lane] = q0; st[kMel + lane + 32] = q1;
             if (c2ok) { st[lane + 64] = s2; st[kMel + lane + 64] = q2; }
-            __syncthreads();
+            JS2T_MIDBAR(4);
             if (tid < kStatsPerTile) {
               float acc = 0.f;
 #pragma unroll
