@@ -2,6 +2,12 @@
 // reference interfaces each entry point replaces.
 #include "../../include/joeys2t_b200.h"
 
+#ifndef JS2T_DEFAULT_APPLY_VARIANT
+#define JS2T_DEFAULT_APPLY_VARIANT 0
+#endif
+#ifndef JS2T_DEFAULT_SIDE_LIMIT
+#define JS2T_DEFAULT_SIDE_LIMIT 0
+#endif
 #include <dlfcn.h>
 #if defined(__x86_64__)
 #include <emmintrin.h>
@@ -66,6 +72,7 @@ struct DeviceGuard {
 struct js2t_ctx {
   int device = 0;
   float* d_tables = nullptr;  // window_half[400] | tw256[256 x float2] | tw512[136 x float2]
+  int* d_side_occ = nullptr;  // [kSideOccInts] CTAs of the side kernel (apply_stream_kernel) resident per SM
   bool tables_set = false;
   // plan descriptors are uploaded on this (non-blocking) stream; every plan records an event behind its
   // upload and every execute stream waits for it, so the upload is formally ordered before the kernels
@@ -81,6 +88,7 @@ struct js2t_ctx {
 namespace {
 
 constexpr size_t kPoolMaxEntries = 16;
+constexpr int kSideOccInts = 1024;  // >= SMs of any device
 constexpr size_t kPoolMaxBytes = size_t(1) << 30;
 
 // smallest idle buffer that fits without wasting more than 4x, else a fresh allocation (64 KB granules)
@@ -152,6 +160,9 @@ struct js2t_plan {
   bool has_masks = false, global_stats_set = false, stats_valid = false;
   bool feature_input = false;  // rows of 80 floats instead of PCM (js2t_plan_create_features)
   int grid_limit = 0;          // tuning only: option "max_ctas"
+  int apply_variant = JS2T_DEFAULT_APPLY_VARIANT;  // option "apply_stream": 1 = persistent TMA-fed side kernel
+  int side_ctas = 0;           // option "side_ctas": CTAs per SM of that kernel (0 = default)
+  int side_limit = JS2T_DEFAULT_SIDE_LIMIT;  // option "side_limit": resident CTAs of that kernel per SM (0 = no limit)
   int dbg_skip = 0;            // tuning only: phases of the fbank kernel to skip (results are wrong)
   unsigned long long* d_dbg = nullptr;  // [n_tiles][4] debug time stamps (option "debug_times")
   // optional instrumentation: CUDA events around the fbank kernel of each execute (ring of slots)
@@ -211,9 +222,12 @@ int js2t_ctx_create(int device, js2t_ctx** out) {
   c->device = device;
   const size_t bytes = (400 + 2 * 256 + 2 * 136) * sizeof(float);
   cudaError_t e = cudaMalloc(&c->d_tables, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_side_occ, sizeof(int) * kSideOccInts);
+  if (e == cudaSuccess) e = cudaMemset(c->d_side_occ, 0, sizeof(int) * kSideOccInts);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     if (c->d_tables) cudaFree(c->d_tables);
+    if (c->d_side_occ) cudaFree(c->d_side_occ);
     delete c;
     return fail(JS2T_ERR_CUDA, "context allocation failed: %s", cudaGetErrorString(e));
   }
@@ -229,6 +243,7 @@ int js2t_ctx_destroy(js2t_ctx* ctx) {
     cudaStreamDestroy(ctx->upload_stream);
   }
   if (ctx->d_tables) cudaFree(ctx->d_tables);
+  if (ctx->d_side_occ) cudaFree(ctx->d_side_occ);
   for (auto& b : ctx->pool) cudaFree(b.second);
   delete ctx;
   return JS2T_OK;
@@ -421,7 +436,7 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
   const size_t o_mv = carve(sizeof(float) * n_utts);
   const size_t o_g = carve(sizeof(float) * 2 * kMel);
   const size_t o_ustats = carve(sizeof(double) * kStatsPerTile * n_utts);
-  const size_t o_sched = carve(sizeof(int) * 2);
+  const size_t o_sched = carve(sizeof(int) * 4);  // fbank kernel [2] | side kernel [2]
   const size_t o_row0 = carve(sizeof(long long) * n_utts);
   DeviceGuard guard(ctx->device);
   cudaError_t e = guard.err;
@@ -455,7 +470,7 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
   // upload_stream in front of ready_ev, which every execute stream waits for (plan_begin).
   e = cudaEventCreateWithFlags(&p->ready_ev, cudaEventDisableTiming);
   cudaStream_t us = ctx->upload_stream;
-  if (e == cudaSuccess) e = cudaMemsetAsync(p->d_sched, 0, sizeof(int) * 2, us);
+  if (e == cudaSuccess) e = cudaMemsetAsync(p->d_sched, 0, sizeof(int) * 4, us);
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(p->d_utts, p->h_utts.data(), sizeof(UttDesc) * n_utts, cudaMemcpyHostToDevice, us);
   if (e == cudaSuccess)
@@ -621,6 +636,11 @@ static ApplyLaunch make_apply(const js2t_plan* plan, float* out_dev, bool shared
   a.cmvn_after = (plan->cmvn_mode != JS2T_CMVN_NONE && !plan->before) ? 1 : 0;
   a.pad_tmax = plan->pad_tmax;
   a.pad_value = plan->pad_value;
+  a.variant = plan->apply_variant;
+  a.side_ctas_per_sm = plan->side_ctas;
+  a.side_sched = plan->d_sched + 2;
+  a.side_occ = plan->ctx->d_side_occ;
+  a.side_limit = plan->side_limit;
   return a;
 }
 
@@ -779,6 +799,18 @@ int js2t_plan_set_option(js2t_plan* plan, const char* name, int value) {
   if (plan == nullptr || name == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
   if (strcmp(name, "max_ctas") == 0) {
     plan->grid_limit = value;
+    return JS2T_OK;
+  }
+  if (strcmp(name, "apply_stream") == 0) {
+    plan->apply_variant = value;  // 0 one CTA per tile | 1 persistent TMA-fed | 2 persistent, warp per tile
+    return JS2T_OK;
+  }
+  if (strcmp(name, "side_ctas") == 0) {
+    plan->side_ctas = value;
+    return JS2T_OK;
+  }
+  if (strcmp(name, "side_limit") == 0) {
+    plan->side_limit = value;
     return JS2T_OK;
   }
   if (strcmp(name, "debug_skip") == 0) {

@@ -116,6 +116,11 @@ struct ApplyLaunch {
   int cmvn_after;           // 1: fill first, then normalise (cmvn.before == False)
   int pad_tmax;
   float pad_value;
+  int variant;           // 0: one CTA per tile (apply_kernel); 1: persistent TMA-fed side kernel (apply_stream_kernel)
+  int side_ctas_per_sm;  // variant 1: grid = this many CTAs per SM (0 = default)
+  int* side_sched;       // variant 1: [2] tile claim counter | CTAs that have left (self-resetting)
+  int* side_occ;         // variant 1: [n_sm] CTAs of the side kernel resident per SM (all plans of the context)
+  int side_limit;        // variant 1: at most this many per SM (0 = no limit)
 };
 
 cudaError_t upload_mel_weights(const float* wu256, const float* wd256, cudaStream_t s);
@@ -125,6 +130,7 @@ cudaError_t launch_fbank(const FbankLaunch& p, cudaStream_t s);
 cudaError_t launch_features(const FbankLaunch& p, cudaStream_t s);  // p.pcm = feature rows
 cudaError_t launch_finalize(const FinalizeLaunch& p, cudaStream_t s);
 cudaError_t launch_apply(const ApplyLaunch& p, cudaStream_t s);
+cudaError_t launch_apply_warp(const ApplyLaunch& p, cudaStream_t s);  // side_kernels.cu
 // accum[0..79] += sum, accum[80..159] += sumsq, accum[160] += frames  (fixed order => deterministic)
 cudaError_t launch_global_accumulate(const double* utt_stats, const UttDesc* utts, int n_utts,
                                      double* accum, cudaStream_t s);
