@@ -526,15 +526,15 @@ constexpr int kMaxEpilogueMasks = 16;
 // host-drawn noise (sum T, 400) is added to every frame's samples before DC removal.  The two frames of a
 // pair then no longer share their samples, so this variant keeps one set of d values per frame; it is
 // slower and not on the benchmarked path.
-// -DJS2T_FBANK_MAXNREG=n caps the registers per thread explicitly (launch bounds and __maxnreg__ exclude
-// each other): below 128 the two resident CTAs leave registers for a co-resident side kernel
-#if defined(JS2T_FBANK_MAXNREG)
-#define JS2T_FBANK_BOUNDS __maxnreg__(JS2T_FBANK_MAXNREG)
-#else
-#define JS2T_FBANK_BOUNDS __launch_bounds__(kThreads, JS2T_MIN_CTAS)
-#endif
-template <int kMode, bool kDither = false>
-__global__ void JS2T_FBANK_BOUNDS fbank_tile_kernel(const FbankLaunch p) {
+// The kernel exists in two register allocations (launch bounds and __maxnreg__ exclude each other):
+//   fbank_tile_kernel      128 registers per thread: two resident CTAs use the whole register file
+//   fbank_tile_kernel_co   112 registers per thread: two resident CTAs leave 2 048 registers per scheduler
+//                          free, which is what the finalize / apply kernels of the PREVIOUS batch need to run
+//                          on the same SMs at the same time (pipelined plans, side_kernels.cu).  178.2 ->
+//                          179.3 us per config-2 launch, no spills (profiles/r2_corun_ab.txt; 120 registers:
+//                          183.3, 104: 186.7, 96: 187.9 with spills).
+template <int kMode, bool kDither>
+__device__ __forceinline__ void fbank_tile_body(const FbankLaunch& p) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* sWin = reinterpret_cast<float*>(smem + kOffWin);
   float2* sTw256 = reinterpret_cast<float2*>(smem + kOffTw256);
@@ -1089,6 +1089,18 @@ __global__ void JS2T_FBANK_BOUNDS fbank_tile_kernel(const FbankLaunch p) {
   }
 }
 
+template <int kMode, bool kDither = false>
+__global__ void __launch_bounds__(kThreads, JS2T_MIN_CTAS) fbank_tile_kernel(const FbankLaunch p) {
+  fbank_tile_body<kMode, kDither>(p);
+}
+#ifndef JS2T_FBANK_CO_REGS
+#define JS2T_FBANK_CO_REGS 112
+#endif
+template <int kMode>
+__global__ void __maxnreg__(JS2T_FBANK_CO_REGS) fbank_tile_kernel_co(const FbankLaunch p) {
+  fbank_tile_body<kMode, false>(p);
+}
+
 // =====================================================================================================
 //  Kernel A': pre-extracted features (the reference's .npy / npy-in-zip branch,
 //  joeynmt/helpers_for_audio.py:100-127) -> same raw layout + per-tile statistics, so that CMVN and
@@ -1122,18 +1134,12 @@ __global__ void __launch_bounds__(kThreads) feature_tile_kernel(const FbankLaunc
 //  Kernel F: per-utterance statistics -> mean / inverse std / SpecAugment fill value
 //  (joeynmt/data_augmentation.py:96-109 CMVN; :43-46 mask value; tokenizers.py:488-493 order)
 // =====================================================================================================
-#ifndef JS2T_FINALIZE_PARTS
-#define JS2T_FINALIZE_PARTS 4
-#endif
-constexpr int kFinalizeParts = JS2T_FINALIZE_PARTS;
-// -DJS2T_FINALIZE_THREADS=n: fewer threads than (parts x columns) loop over the work items (the co-resident
-// variant runs 128 threads = one warp per scheduler next to the fbank kernel's two CTAs)
-#ifndef JS2T_FINALIZE_THREADS
-#define JS2T_FINALIZE_THREADS (JS2T_FINALIZE_PARTS * 160)
-#endif
-constexpr int kFinalizeThreads = JS2T_FINALIZE_THREADS;
-static_assert(kFinalizeThreads >= kMel, "one thread per mel bin after the column sums");
+// Two shapes: <4, 640> when the kernel has the GPU to itself (four threads per statistics column), and
+// <1, 128> for pipelined plans, where it runs NEXT TO the fbank kernel of the following batch and has to fit
+// into the 2 048 registers per scheduler that kernel's two resident CTAs leave free (one warp per scheduler).
+template <int kFinalizeParts, int kFinalizeThreads>
 __global__ void __launch_bounds__(kFinalizeThreads) finalize_utt_kernel(const FinalizeLaunch p) {
+  static_assert(kFinalizeThreads >= kMel, "one thread per mel bin after the column sums");
   const int u = blockIdx.x;
   const int b = threadIdx.x;  // mel bin (threads >= 80 only help with the column sums)
   pdl_launch();
@@ -1351,222 +1357,6 @@ __global__ void __launch_bounds__(kApplyThreads, JS2T_APPLY_MIN_CTAS) apply_kern
 }
 
 // =====================================================================================================
-//  Kernel C': the same in-place CMVN + SpecAugment fill as a PERSISTENT, TMA-FED SIDE KERNEL.
-//  The fbank kernel is bound by the SM's FP32 pipe and shared-memory crossbar and leaves HBM 90 % idle; this
-//  pass is a pure stream.  So that the two can run on the same SMs at the same time, this variant fits into what
-//  the fbank kernel's two resident CTAs leave free — 2 048 registers per scheduler (fbank at 112 registers per
-//  thread) and 31 KB of shared memory: 80 threads = 3 warps of <= 64 registers, and the data in flight lives in
-//  shared memory, not in registers — two slots of one tile each (rows + the utterance's mean / 1/std + its mask
-//  table), filled by bulk async copies (TMA 1-D) that are issued one tile ahead by thread 0.  Work = tiles
-//  blockIdx.x, + gridDim.x, ... counted from the NEWEST tile (see apply_kernel); thread (r0, c4) owns float4
-//  column c4 of rows r0 + 4 j.  Results go straight from registers to HBM (coalesced 16-byte stores).
-// =====================================================================================================
-#ifndef JS2T_SIDE_CTAS_DEFAULT
-#define JS2T_SIDE_CTAS_DEFAULT 4
-#endif
-constexpr int kSideThreads = 80;                       // 4 row groups x 20 float4 columns
-constexpr int kSideRowStep = kSideThreads / (kMel / 4);  // 4
-constexpr int kSideRows = kTileFrames / kSideRowStep;    // 8 rows per thread
-constexpr int kSideSlots = 2;
-constexpr int kSideMaxMasks = 15;  // mask table of the tile's utterance: fetched by one warp (2 n + 1 <= 32 words)
-struct __align__(16) SideSlot {
-  float rows[kTileFrames * kMel];
-  float mean[kMel];
-  float istd[kMel];
-  int masks[2 * kSideMaxMasks + 2];  // (start, width) pairs, then the fill value (as bits)
-};
-static_assert(sizeof(SideSlot) % 16 == 0, "slots are bulk-copy targets");
-constexpr int kSideSmemBytes = kSideSlots * (int)sizeof(SideSlot);
-
-#ifndef JS2T_SIDE_MIN_CTAS
-#define JS2T_SIDE_MIN_CTAS 10
-#endif
-__global__ void __launch_bounds__(kSideThreads, JS2T_SIDE_MIN_CTAS) apply_stream_kernel(const ApplyLaunch p) {
-  extern __shared__ __align__(16) unsigned char side_smem[];
-  SideSlot* slots = reinterpret_cast<SideSlot*>(side_smem);
-  __shared__ __align__(8) unsigned long long bar[kSideSlots];
-  __shared__ __align__(16) TileDesc hdr[2 * kSideSlots];  // descriptors of the tiles in flight (ring of 4)
-  __shared__ int s_go;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int c4 = tid % (kMel / 4), r0 = tid / (kMel / 4);
-  // At most side_limit CTAs of this kernel per SM, whichever launch they belong to: the block scheduler puts
-  // several on an SM that happens to be empty, and that SM could then not take its two fbank CTAs.  The
-  // surplus CTAs leave at once; tiles are claimed dynamically, so the ones that stay do all the work.
-  unsigned smid;
-  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-  if (tid == 0) {
-    for (int i = 0; i < kSideSlots; ++i) mbar_init(bar + i, 1);
-    int go = 1;
-    if (p.side_limit > 0) {
-      go = atomicAdd(p.side_occ + smid, 1) < p.side_limit ? 1 : 0;
-      if (!go) atomicSub(p.side_occ + smid, 1);
-    }
-    s_go = go;
-  }
-  const int n_masks = p.masks != nullptr ? p.n_fmask + p.n_tmask : 0;
-#if defined(JS2T_SIDE_DBG)
-  constexpr bool kNoLoad = (JS2T_SIDE_DBG & 1) != 0, kNoStore = (JS2T_SIDE_DBG & 2) != 0;  // timing probes only
-  constexpr bool kNoWork = (JS2T_SIDE_DBG & 4) != 0, kNoSync = (JS2T_SIDE_DBG & 8) != 0;
-  constexpr bool kSleep = (JS2T_SIDE_DBG & 32) != 0;
-#else
-  constexpr bool kNoLoad = false, kNoStore = false, kNoWork = false, kNoSync = false, kSleep = false;
-#endif
-  __syncthreads();
-  const bool go = s_go != 0;
-  pdl_wait();  // statistics of the finalize kernel and, through it, the raw rows
-
-  // warp 0 starts the copies of the tile with claim number c (tile n_tiles - 1 - c: newest first) for this
-  // CTA's i-th iteration into slot i % 2: rows, mean, 1/std by bulk async copy on the slot's mbarrier
-  // (lane 0), the mask table by 4-byte cp.async (lanes 0 .. 2 n_masks).  utt < 0 marks the end of the work.
-  auto issue = [&](int i, const TileDesc& td) {
-    SideSlot& sl = slots[i % kSideSlots];
-    if (lane == 0) {
-      hdr[i % (2 * kSideSlots)] = td;
-      if (td.utt >= 0 && td.nf > 0 && !kNoLoad) {
-        const long long so = p.shared_stats ? 0 : (long long)td.utt * kMel;
-        unsigned long long* b = bar + i % kSideSlots;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)),
-                     "r"((unsigned)(td.nf * kMel * 4 + 2 * kMel * 4))
-                     : "memory");
-        auto bulk = [&](void* dst, const void* src, unsigned bytes) {
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                           smem_u32(dst)),
-                       "l"(src), "r"(bytes), "r"(smem_u32(b))
-                       : "memory");
-        };
-        bulk(sl.rows, p.out + td.out_row0 * (long long)kMel, (unsigned)(td.nf * kMel * 4));
-        bulk(sl.mean, p.mean + so, kMel * 4);
-        bulk(sl.istd, p.istd + so, kMel * 4);
-      }
-    }
-    if (n_masks > 0) {
-      const int utt = __shfl_sync(0xffffffffu, td.utt, 0);
-      const int nf = __shfl_sync(0xffffffffu, (int)td.nf, 0);
-      if (utt >= 0 && nf > 0 && lane <= 2 * n_masks) {
-        const void* src = lane < 2 * n_masks ? (const void*)(p.masks + (long long)utt * 2 * n_masks + lane)
-                                             : (const void*)(p.mask_value + utt);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&sl.masks[lane])), "l"(src) : "memory");
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  // lane 0 of warp 0: the claim pipeline.  desc_b = descriptor of the tile to issue next (its load was started
-  // one iteration ago), claim_a = claim number whose descriptor is loaded next (its atomic was started one
-  // iteration ago): neither the atomic nor the descriptor load is waited for where it is issued.
-  TileDesc desc_b = {};
-  int claim_a = 0;
-  auto load_desc = [&](int claim) {
-    TileDesc d = {};
-    d.utt = -1;
-    if (claim < p.n_tiles) d = p.tiles[p.n_tiles - 1 - claim];
-    return d;
-  };
-  if (go && tid < 32) {
-    int base = 0;
-    if (lane == 0) base = atomicAdd(p.side_sched, kSideSlots + 1);
-    for (int i = 0; i < kSideSlots; ++i) {
-      if (lane == 0) desc_b = load_desc(base + i);
-      issue(i, desc_b);
-    }
-    if (lane == 0) {
-      desc_b = load_desc(base + kSideSlots);
-      claim_a = atomicAdd(p.side_sched, 1);
-    }
-    asm volatile("cp.async.wait_group 1;" ::: "memory");  // the first tile's mask table has landed
-  }
-  __syncthreads();
-
-  const float4 pad = make_float4(p.pad_value, p.pad_value, p.pad_value, p.pad_value);
-  const bool after = p.cmvn_after != 0;
-  unsigned phase = 0;  // bit s = parity the next wait on slot s uses
-  for (int i = 0; go; ++i) {
-    const int s = i % kSideSlots;
-    SideSlot& sl = slots[s];
-    const TileDesc td = hdr[i % (2 * kSideSlots)];
-    if (td.utt < 0) break;  // no tiles left (claims are handed out in order: every later one is past the end too)
-    const int nf = td.nf, rows = td.rows;
-    float4* o4 = reinterpret_cast<float4*>(p.out + td.out_row0 * (long long)kMel) + c4;
-    if (kSleep) __nanosleep(500);
-    if (kNoWork) {
-    } else if (nf > 0) {
-      if (!kNoLoad) mbar_wait(bar + s, (phase >> s) & 1u);
-      phase ^= 1u << s;
-      const float4 mu = reinterpret_cast<const float4*>(sl.mean)[c4];
-      const float4 is = reinterpret_cast<const float4*>(sl.istd)[c4];
-      // (the loops below stay rolled on purpose: this kernel runs next to the fbank kernel, whose own loop
-      // already overflows the instruction caches, so its code footprint costs the fbank kernel time)
-      unsigned cm = 0, tm = 0;
-      float mv = 0.f;
-      if (n_masks > 0) {
-#pragma unroll 1
-        for (int m = 0; m < n_masks; ++m) {
-          const int m0 = sl.masks[2 * m];
-          const unsigned w = (unsigned)sl.masks[2 * m + 1];
-          if (m < p.n_fmask) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) cm |= (unsigned)((unsigned)(4 * c4 + j - m0) < w) << j;
-          } else {
-#pragma unroll
-            for (int k = 0; k < kSideRows; ++k) tm |= (unsigned)((unsigned)(td.frame0 + r0 + kSideRowStep * k - m0) < w) << k;
-          }
-        }
-        mv = __int_as_float(sl.masks[2 * n_masks]);
-      }
-#pragma unroll 1
-      for (int k = 0; k < kSideRows; ++k) {
-        const int f = r0 + kSideRowStep * k;
-        if (f >= rows) break;
-        float4 y = pad;
-        if (f < nf) {
-          float4 x = reinterpret_cast<const float4*>(sl.rows)[f * (kMel / 4) + c4];
-          const unsigned m = ((tm >> k) & 1u) ? 0xfu : cm;
-          if (after) {  // SpecAugment saw the raw log-mel; CMVN normalises the filled cells too
-            x.x = (m & 1u) ? mv : x.x;
-            x.y = (m & 2u) ? mv : x.y;
-            x.z = (m & 4u) ? mv : x.z;
-            x.w = (m & 8u) ? mv : x.w;
-          }
-          y = make_float4((x.x - mu.x) * is.x, (x.y - mu.y) * is.y, (x.z - mu.z) * is.z, (x.w - mu.w) * is.w);
-          if (!after) {
-            y.x = (m & 1u) ? mv : y.x;
-            y.y = (m & 2u) ? mv : y.y;
-            y.z = (m & 4u) ? mv : y.z;
-            y.w = (m & 8u) ? mv : y.w;
-          }
-        }
-        if (!kNoStore || y.x == 12345.f) o4[f * (kMel / 4)] = y;
-      }
-    } else {
-#pragma unroll 1
-      for (int k = 0; k < kSideRows; ++k) {
-        const int f = r0 + kSideRowStep * k;
-        if (f < rows) o4[f * (kMel / 4)] = pad;
-      }
-    }
-    if (!kNoSync) __syncthreads();  // the slot and its header have been read by everyone
-    if (tid < 32) {
-      issue(i + kSideSlots, desc_b);
-      if (lane == 0) {
-        desc_b = load_desc(claim_a);
-        claim_a = claim_a < p.n_tiles ? atomicAdd(p.side_sched, 1) : claim_a;
-      }
-      asm volatile("cp.async.wait_group 1;" ::: "memory");  // mask table of the tile processed next
-    }
-    if (!kNoSync) __syncthreads();  // header / mask table of the next tile visible to all
-  }
-  pdl_launch();
-  // the last CTA to leave re-arms the claim counter for the next launch and the SM slot is given back
-  if (tid == 0) {
-    if (go && p.side_limit > 0) atomicSub(p.side_occ + smid, 1);
-    if (atomicAdd(p.side_sched + 1, 1) == (int)gridDim.x - 1) {
-      p.side_sched[0] = 0;
-      p.side_sched[1] = 0;
-    }
-  }
-}
-
-// =====================================================================================================
 //  Global CMVN statistics (extension named by north_star; formula of data_augmentation.py:98-105)
 // =====================================================================================================
 __global__ void __launch_bounds__(kStatsPerTile + 32) global_accumulate_kernel(
@@ -1648,15 +1438,16 @@ int fbank_persistent_grid() {
     cudaFuncSetAttribute(fbank_tile_kernel<kModeRaw>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     cudaFuncSetAttribute(fbank_tile_kernel<kModeNormKnown>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     cudaFuncSetAttribute(fbank_tile_kernel<kModeRaw, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-#if defined(JS2T_SIDE_CARVEOUT) && JS2T_SIDE_CARVEOUT
-    // the side kernels ask for the same shared-memory carve-out as the fbank kernel: an SM only runs CTAs
-    // of kernels whose carve-out matches its current configuration
-    cudaFuncSetAttribute(apply_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(finalize_utt_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(fbank_tile_kernel<kModeRaw>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(fbank_tile_kernel<kModeNormKnown>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(fbank_tile_kernel<kModeRaw, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(fbank_tile_kernel_co<kModeRaw>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(fbank_tile_kernel_co<kModeNormKnown>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    // the kernels that may share an SM (pipelined plans: finalize / apply of one batch next to the fbank kernel
+    // of the next) must agree on the shared-memory carve-out: an SM only runs CTAs of kernels whose carve-out
+    // matches its current configuration
+#if JS2T_FBANK_CARVEOUT >= 0
+    cudaFuncSetAttribute(fbank_tile_kernel_co<kModeRaw>, cudaFuncAttributePreferredSharedMemoryCarveout, JS2T_FBANK_CARVEOUT);
+    cudaFuncSetAttribute(fbank_tile_kernel_co<kModeNormKnown>, cudaFuncAttributePreferredSharedMemoryCarveout, JS2T_FBANK_CARVEOUT);
 #endif
+    cudaFuncSetAttribute(finalize_utt_kernel<1, 128>, cudaFuncAttributePreferredSharedMemoryCarveout, JS2T_SIDE_CARVEOUT);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fbank_tile_kernel<kModeRaw>, kThreads, kSmemBytes);
     if (occ < 1) occ = 1;
     g_fbank_grid = occ * n_sm;  // every CTA resident at once: one wave, persistent
@@ -1666,7 +1457,7 @@ int fbank_persistent_grid() {
 
 // launch with programmatic stream serialization (see pdl_wait / pdl_launch)
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+static cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                               Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -1675,7 +1466,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = JS2T_PDL ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = (JS2T_PDL && pdl) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
@@ -1688,42 +1479,33 @@ cudaError_t launch_fbank(const FbankLaunch& p, cudaStream_t s) {
   const int grid = p.n_tiles < full ? p.n_tiles : full;
   if (p.dither != nullptr) {  // compatibility mode: raw epilogue only (capi.cu routes CMVN through the apply kernel)
     if (p.epilogue != kEpiRaw) return cudaErrorInvalidValue;
-    return launch_pdl(fbank_tile_kernel<kModeRaw, true>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
+    return launch_pdl(p.pdl != 0, fbank_tile_kernel<kModeRaw, true>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
+  }
+  if (p.co_resident) {  // pipelined plans: the allocation that leaves room for the previous batch's side kernels
+    if (p.epilogue == kEpiNormKnown)
+      return launch_pdl(p.pdl != 0, fbank_tile_kernel_co<kModeNormKnown>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
+    return launch_pdl(p.pdl != 0, fbank_tile_kernel_co<kModeRaw>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
   }
   if (p.epilogue == kEpiNormKnown)
-    return launch_pdl(fbank_tile_kernel<kModeNormKnown>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
-  return launch_pdl(fbank_tile_kernel<kModeRaw>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
+    return launch_pdl(p.pdl != 0, fbank_tile_kernel<kModeNormKnown>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
+  return launch_pdl(p.pdl != 0, fbank_tile_kernel<kModeRaw>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
 }
 
 cudaError_t launch_features(const FbankLaunch& p, cudaStream_t s) {
   if (p.n_tiles <= 0) return cudaSuccess;
-  return launch_pdl(feature_tile_kernel, dim3(p.n_tiles), dim3(kThreads), 0, s, p);
+  return launch_pdl(p.pdl != 0, feature_tile_kernel, dim3(p.n_tiles), dim3(kThreads), 0, s, p);
 }
 
 cudaError_t launch_finalize(const FinalizeLaunch& p, cudaStream_t s) {
   if (p.n_utts <= 0) return cudaSuccess;
-  return launch_pdl(finalize_utt_kernel, dim3(p.n_utts), dim3(kFinalizeThreads), 0, s, p);
+  if (p.small) return launch_pdl(p.pdl != 0, finalize_utt_kernel<1, 128>, dim3(p.n_utts), dim3(128), 0, s, p);
+  return launch_pdl(p.pdl != 0, finalize_utt_kernel<4, 640>, dim3(p.n_utts), dim3(640), 0, s, p);
 }
 
 cudaError_t launch_apply(const ApplyLaunch& p, cudaStream_t s) {
   if (p.n_tiles <= 0) return cudaSuccess;
-  const int n_masks = p.masks != nullptr ? p.n_fmask + p.n_tmask : 0;
-  if (p.variant == 2) return launch_apply_warp(p, s);
-  if (p.variant == 1 && n_masks <= kSideMaxMasks) {
-    static int n_sm = 0;
-    if (n_sm == 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-      cudaFuncSetAttribute(apply_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSideSmemBytes);
-      cudaFuncSetAttribute(apply_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                           cudaSharedmemCarveoutMaxShared);
-    }
-    const int per_sm = p.side_ctas_per_sm > 0 ? p.side_ctas_per_sm : JS2T_SIDE_CTAS_DEFAULT;
-    const int grid = p.n_tiles < per_sm * n_sm ? p.n_tiles : per_sm * n_sm;
-    return launch_pdl(apply_stream_kernel, dim3(grid), dim3(kSideThreads), kSideSmemBytes, s, p);
-  }
-  return launch_pdl(apply_kernel, dim3(p.n_tiles), dim3(kApplyThreads), 0, s, p);
+  if (p.variant == 2) return launch_apply_warp(p, s);  // side_kernels.cu
+  return launch_pdl(p.pdl != 0, apply_kernel, dim3(p.n_tiles), dim3(kApplyThreads), 0, s, p);
 }
 
 cudaError_t launch_global_accumulate(const double* utt_stats, const UttDesc* utts, int n_utts,

@@ -1,6 +1,24 @@
-// Side kernel of the audio front-end (see apply_kernel in fbank_kernels.cu for what it computes): the in-place
-// CMVN + SpecAugment pass as a small persistent kernel that can run on the same SMs as the fbank kernel.  It
-// lives in its own translation unit (its own code region in the binary), apart from the fbank kernel.
+// Side kernel of JoeyS2T's audio front-end: the in-place CMVN + SpecAugment pass
+//   joeynmt/data_augmentation.py:96-109  CMVN.__call__      (x - mean) / std per mel bin
+//   joeynmt/data_augmentation.py:38-73   SpecAugment        host-drawn masks filled with the mask value
+//   joeynmt/helpers_for_audio.py:130-170 pad_features       padding rows of the padded layout
+// as a small persistent kernel that runs ON THE SAME SMs, AT THE SAME TIME as the fbank kernel of the next
+// batch (pipelined plans: consecutive batches alternate between streams).  The fbank kernel is bound by the
+// SM's FP32 pipe and shared-memory crossbar and leaves HBM 90 % idle; this pass is a pure HBM stream, so the
+// two overlap instead of queueing behind each other.  What the measurements on the B200 say it takes
+// (profiles/r2_corun_ab.txt):
+//   * footprint: the fbank kernel's two resident CTAs (112 registers per thread) leave 2 048 registers per
+//     scheduler and 31 KB of shared memory: 128 threads = one warp per scheduler at <= 64 registers, no
+//     shared memory; every kernel of the path asks for the same (maximum) shared-memory carve-out;
+//   * one CTA of a launch per SM (residency gate below): the block scheduler otherwise stacks several on an SM
+//     that is momentarily empty, which then cannot take its two fbank CTAs; no programmatic dependent launch
+//     (early-launched dependents squat on the free resources);
+//   * every warp-wide load / store covers 512 CONTIGUOUS bytes.  A first version with 20 active lanes per
+//     80-float row (+ 12 lanes shadowing the last one) cost the co-resident fbank kernel 23 us per batch, this
+//     one 5-8 us; a TMA-fed shared-memory ring (data in flight in shared memory instead of registers) cost
+//     35-50 us — its shared-memory traffic and its code footprint both land on the fbank kernel's bottlenecks
+//     (shared-memory crossbar, instruction fetch);
+//   * a loop body of a few hundred bytes, kept rolled.
 #include "js2t_internal.h"
 
 namespace js2t {
@@ -19,37 +37,24 @@ __device__ __forceinline__ void pdl_launch() {
 #endif
 }
 #ifndef JS2T_SIDE_CTAS_DEFAULT
-#define JS2T_SIDE_CTAS_DEFAULT 4
+#define JS2T_SIDE_CTAS_DEFAULT 2  // CTAs launched per SM; with a residency limit the surplus ones leave at once
 #endif
 
 // =====================================================================================================
-//  Kernel C'': the side kernel without shared memory.  Every WARP is an independent worker: it claims a tile,
-//  its lanes 0..19 own one float4 column each and walk the 32 rows in four batches of eight 16-byte loads
-//  (so the data in flight sits in registers: 20 lanes x 8 x 16 B per warp), normalise and store.  No block
-//  barrier, no shared-memory traffic (the fbank kernel next to it is bound by the shared-memory crossbar),
-//  a loop body of a few hundred bytes (the fbank kernel's own loop overflows the instruction caches).
+//  Every WARP is an independent worker: it claims a tile (dynamic claims, newest tile first — see apply_kernel),
+//  normalises its 32 x 80 floats in place and claims the next.  No block barrier, no shared memory; the data
+//  in flight sits in registers (four 16-byte loads per lane).
 // =====================================================================================================
-// how the rows are loaded / stored: 0 = default caching, 1 = streaming (evict-first) hints
-#ifndef JS2T_SIDE_MEMOP
-#define JS2T_SIDE_MEMOP 0
-#endif
-#if JS2T_SIDE_MEMOP == 1
-#define JS2T_SIDE_LOAD(ptr) __ldcs(ptr)
-#define JS2T_SIDE_STORE(ptr, v) __stcs(ptr, v)
-#elif JS2T_SIDE_MEMOP == 2
-#define JS2T_SIDE_LOAD(ptr) __ldcg(ptr)
-#define JS2T_SIDE_STORE(ptr, v) __stcg(ptr, v)
-#else
 #define JS2T_SIDE_LOAD(ptr) (*(ptr))
 #define JS2T_SIDE_STORE(ptr, v) (*(ptr) = (v))
-#endif
 constexpr int kWarpSideThreads = 128;  // four independent warps, one per scheduler
 __global__ void __launch_bounds__(kWarpSideThreads, 8) apply_warp_kernel(const ApplyLaunch p) {
   __shared__ int s_go;
   const int tid = threadIdx.x, lane = tid & 31;
-  // At most side_limit CTAs of this kernel per SM, whichever launch they belong to: the block scheduler puts
-  // several on an SM that happens to be empty, and that SM could then not take its two fbank CTAs.  The
-  // surplus CTAs leave at once; tiles are claimed dynamically, so the ones that stay do all the work.
+  // At most side_limit CTAs of this launch per SM: the block scheduler puts several on an SM that happens to be
+  // empty, and that SM could then not take its two fbank CTAs.  The surplus CTAs leave at once; tiles are
+  // claimed dynamically, so the ones that stay do all the work (the first CTA to arrive on an SM always
+  // stays, so every launch has workers).
   unsigned smid;
   asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
   if (tid == 0) {
@@ -180,7 +185,7 @@ cudaError_t launch_apply_warp(const ApplyLaunch& p, cudaStream_t s) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(apply_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(apply_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, JS2T_SIDE_CARVEOUT);
   }
   const int per_sm = p.side_ctas_per_sm > 0 ? p.side_ctas_per_sm : JS2T_SIDE_CTAS_DEFAULT;
   const int warps = (p.n_tiles + 3) / 4;
@@ -192,7 +197,7 @@ cudaError_t launch_apply_warp(const ApplyLaunch& p, cudaStream_t s) {
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = JS2T_PDL ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = (JS2T_PDL && p.pdl) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, apply_warp_kernel, p);

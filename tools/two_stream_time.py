@@ -24,7 +24,9 @@ for r in range(R):
 hours = sum(len(w) for w in synthetic.pooled_batch(256, seed=1234, lo=10.0, hi=15.0)) / 16000 / 3600
 
 
-def timeit(n_streams, n=40, reps=3, prio=False):
+def timeit(n_streams, n=40, reps=3, prio=False, pipelined=None):
+    for p_, _, _ in sets:
+        p_.set_pipelined(n_streams > 1 if pipelined is None else pipelined)
     streams = [torch.cuda.Stream(priority=(-1 if (prio and i == 1) else 0)) for i in range(n_streams)]
     best = 1e9
     main = torch.cuda.current_stream()
@@ -54,7 +56,7 @@ def timeit(n_streams, n=40, reps=3, prio=False):
 
 label = sys.argv[1] if len(sys.argv) > 1 else os.environ.get("JS2T_LIB", "product")
 one = timeit(1)
-two = timeit(2)
-four = timeit(4)
-print(f"{label:28s} utterance CMVN step: 1 stream {one:7.1f} us ({hours / one * 1e6:6.0f} h/s) | 2 streams {two:7.1f} us "
-      f"({hours / two * 1e6:6.0f} h/s) | 4 streams {four:7.1f} us ({hours / four * 1e6:6.0f} h/s)")
+res = [timeit(k) for k in (2, 3, 4)]
+np2 = timeit(2, pipelined=False)
+print(f"{label:28s} utterance CMVN step: 1 stream {one:7.1f} us ({hours / one * 1e6:6.0f} h/s) | pipelined plans on 2 / 3 / 4 streams "
+      + " / ".join(f"{t:6.1f}" for t in res) + f" us ({hours / min(res) * 1e6:6.0f} h/s) | 2 streams, plans not pipelined {np2:6.1f} us")
