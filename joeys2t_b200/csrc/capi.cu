@@ -731,16 +731,14 @@ static int run_pipeline(js2t_plan* plan, const void* in_dev, float* out_dev, cud
     const size_t slots = plan->prof_ev.size() / 2;
     const size_t slot = slots ? (size_t)(plan->prof_calls % (long long)slots) : 0;
     if (slots) cudaEventRecord(plan->prof_ev[2 * slot], stream);
-    cudaError_t e = from_pcm ? launch_fbank(fl, stream) : launch_features(fl, stream);
+    FbankLaunch fl2 = fl;
+    if (chain_lk.owns_lock()) fl2.started = cx->chain_ev[cx->chain_next % cx->chain_ev.size()];
+    cudaError_t e = from_pcm ? launch_fbank(fl2, stream) : launch_features(fl2, stream);
     if (slots) {
       cudaEventRecord(plan->prof_ev[2 * slot + 1], stream);
       plan->prof_calls++;
     }
-    if (chain_lk.owns_lock() && e == cudaSuccess) {
-      cudaEvent_t ev = cx->chain_ev[cx->chain_next++ % cx->chain_ev.size()];
-      e = cudaEventRecord(ev, stream);
-      cx->chain_last = ev;
-    }
+    if (chain_lk.owns_lock() && e == cudaSuccess) cx->chain_last = cx->chain_ev[cx->chain_next++ % cx->chain_ev.size()];
     return e;
   };
   // (1) nothing data-dependent after the log-mel: one kernel, one pass over HBM
@@ -774,9 +772,9 @@ static int run_pipeline(js2t_plan* plan, const void* in_dev, float* out_dev, cud
   JS2T_CUDA(launch_main(f));
   const bool shared = (mode == JS2T_CMVN_GLOBAL);
   FinalizeLaunch z = make_finalize(plan, out_dev, shared);
-  JS2T_CUDA(launch_finalize(z, stream));
+  if (!(plan->dbg_skip & 0x200)) JS2T_CUDA(launch_finalize(z, stream));  // (timing probes: 0x100 no apply, 0x200 no finalize)
   plan->stats_valid = true;
-  if (mode != JS2T_CMVN_STATS_ONLY) {
+  if (mode != JS2T_CMVN_STATS_ONLY && !(plan->dbg_skip & 0x100)) {
     ApplyLaunch a = make_apply(plan, out_dev, shared);
     JS2T_CUDA(launch_apply(a, stream));
   }

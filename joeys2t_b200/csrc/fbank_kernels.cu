@@ -1456,19 +1456,29 @@ int fbank_persistent_grid() {
 }
 
 // launch with programmatic stream serialization (see pdl_wait / pdl_launch)
+// `started` (optional): a programmatic event that fires once every CTA of the grid has issued
+// griddepcontrol.launch_dependents (the fbank kernel does so on entry), i.e. when the whole persistent grid is
+// resident — what the fbank launch of the NEXT pipelined batch, on another stream, waits for
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
-                              Args&&... args) {
+static cudaError_t launch_pdl(bool pdl, cudaEvent_t started, void (*kernel)(KArgs...), dim3 grid, dim3 block,
+                              size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = (JS2T_PDL && pdl) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (started != nullptr) {
+    attr[1].id = cudaLaunchAttributeProgrammaticEvent;
+    attr[1].val.programmaticEvent.event = started;
+    attr[1].val.programmaticEvent.flags = 0;
+    attr[1].val.programmaticEvent.triggerAtBlockStart = 0;
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
@@ -1479,33 +1489,33 @@ cudaError_t launch_fbank(const FbankLaunch& p, cudaStream_t s) {
   const int grid = p.n_tiles < full ? p.n_tiles : full;
   if (p.dither != nullptr) {  // compatibility mode: raw epilogue only (capi.cu routes CMVN through the apply kernel)
     if (p.epilogue != kEpiRaw) return cudaErrorInvalidValue;
-    return launch_pdl(p.pdl != 0, fbank_tile_kernel<kModeRaw, true>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
+    return launch_pdl(p.pdl != 0, nullptr, fbank_tile_kernel<kModeRaw, true>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
   }
   if (p.co_resident) {  // pipelined plans: the allocation that leaves room for the previous batch's side kernels
     if (p.epilogue == kEpiNormKnown)
-      return launch_pdl(p.pdl != 0, fbank_tile_kernel_co<kModeNormKnown>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
-    return launch_pdl(p.pdl != 0, fbank_tile_kernel_co<kModeRaw>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
+      return launch_pdl(p.pdl != 0, p.started, fbank_tile_kernel_co<kModeNormKnown>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
+    return launch_pdl(p.pdl != 0, p.started, fbank_tile_kernel_co<kModeRaw>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
   }
   if (p.epilogue == kEpiNormKnown)
-    return launch_pdl(p.pdl != 0, fbank_tile_kernel<kModeNormKnown>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
-  return launch_pdl(p.pdl != 0, fbank_tile_kernel<kModeRaw>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
+    return launch_pdl(p.pdl != 0, nullptr, fbank_tile_kernel<kModeNormKnown>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
+  return launch_pdl(p.pdl != 0, nullptr, fbank_tile_kernel<kModeRaw>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
 }
 
 cudaError_t launch_features(const FbankLaunch& p, cudaStream_t s) {
   if (p.n_tiles <= 0) return cudaSuccess;
-  return launch_pdl(p.pdl != 0, feature_tile_kernel, dim3(p.n_tiles), dim3(kThreads), 0, s, p);
+  return launch_pdl(p.pdl != 0, nullptr, feature_tile_kernel, dim3(p.n_tiles), dim3(kThreads), 0, s, p);
 }
 
 cudaError_t launch_finalize(const FinalizeLaunch& p, cudaStream_t s) {
   if (p.n_utts <= 0) return cudaSuccess;
-  if (p.small) return launch_pdl(p.pdl != 0, finalize_utt_kernel<1, 128>, dim3(p.n_utts), dim3(128), 0, s, p);
-  return launch_pdl(p.pdl != 0, finalize_utt_kernel<4, 640>, dim3(p.n_utts), dim3(640), 0, s, p);
+  if (p.small) return launch_pdl(p.pdl != 0, nullptr, finalize_utt_kernel<1, 128>, dim3(p.n_utts), dim3(128), 0, s, p);
+  return launch_pdl(p.pdl != 0, nullptr, finalize_utt_kernel<4, 640>, dim3(p.n_utts), dim3(640), 0, s, p);
 }
 
 cudaError_t launch_apply(const ApplyLaunch& p, cudaStream_t s) {
   if (p.n_tiles <= 0) return cudaSuccess;
   if (p.variant == 2) return launch_apply_warp(p, s);  // side_kernels.cu
-  return launch_pdl(p.pdl != 0, apply_kernel, dim3(p.n_tiles), dim3(kApplyThreads), 0, s, p);
+  return launch_pdl(p.pdl != 0, nullptr, apply_kernel, dim3(p.n_tiles), dim3(kApplyThreads), 0, s, p);
 }
 
 cudaError_t launch_global_accumulate(const double* utt_stats, const UttDesc* utts, int n_utts,

@@ -78,6 +78,7 @@ struct FbankLaunch {
   const float* dither;
   const long long* dither_row0;
   int pdl;         // 1: launched with programmatic stream serialization (single-stream plans)
+  cudaEvent_t started;  // host side only: programmatic event "the whole grid is resident" (pipelined plans) or nullptr
   int co_resident; // 1: the 112-register build that leaves room for side kernels on the same SM (pipelined plans)
   int grid_limit;  // tuning only: cap on the persistent grid (0 = all resident CTAs)
   int dbg_skip;  // tuning only: bit0 staging, bit1 FFT phase, bit2 mel, bit3 store, bit4 butterflies, bit5 exchange

@@ -15,6 +15,7 @@ S = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 60
 LIMIT = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 CTAS = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+SKIP = int(sys.argv[5], 0) if len(sys.argv) > 5 else 0
 R = 4
 sets = []
 for r in range(R):
@@ -25,11 +26,12 @@ for r in range(R):
     plan.set_pipelined(S > 1)
     plan.set_option("side_limit", LIMIT)
     plan.set_option("side_ctas", CTAS)
+    plan.set_option("debug_skip", SKIP)
     sets.append((plan, packed.to_device(), [plan.empty_output() for _ in range(6)]))
 streams = [torch.cuda.Stream() for _ in range(S)]
 main = torch.cuda.current_stream()
-print(f'side_limit {LIMIT} side_ctas {CTAS or "default"}')
-for rep in range(5):
+print(f'side_limit {LIMIT} side_ctas {CTAS or "default"} skip {SKIP:#x}')
+for rep in range(3):
     for i in range(8):
         p, d, o = sets[i % R]
         with torch.cuda.stream(streams[i % R % S]):

@@ -55,6 +55,9 @@ def timeit(n_streams, n=40, reps=3, prio=False, pipelined=None):
 
 
 label = sys.argv[1] if len(sys.argv) > 1 else os.environ.get("JS2T_LIB", "product")
+if len(sys.argv) > 2:  # timing probes: 0x100 no apply, 0x200 no finalize
+    for p_, _, _ in sets:
+        p_.set_option("debug_skip", int(sys.argv[2], 0))
 one = timeit(1)
 res = [timeit(k) for k in (2, 3, 4)]
 np2 = timeit(2, pipelined=False)
