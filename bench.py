@@ -12,21 +12,15 @@ One process per GPU (torchrun for N > 1: RANK / LOCAL_RANK / WORLD_SIZE from the
 Every rank processes its own batches (utterances are independent: no data-path collective, weak
 scaling).  A "step" is one pass of the hot path (fbank -> utterance CMVN) over one batch.
 
-* ``value``     whole-job audio-hours/sec with PCM resident in HBM, CUDA-event timed, max over ranks.
-                Consecutive steps alternate between ``--streams`` streams (pipelined plans): the
-                statistics / CMVN kernels of one step — a pure HBM stream — then run on the same SMs, at
-                the same time, as the fbank kernel of the next step, which is FP32 / shared-memory
-                bound and leaves HBM idle.  Every step runs all of its kernels on its own buffers;
-                ``details.ms_per_step_single_stream`` is the same loop on one stream
+* ``value``     whole-job audio-hours/sec with PCM resident in HBM, CUDA-event timed, max over ranks
 * ``e2e``       same metric through the public host API: pinned host PCM -> H2D -> kernels -> D2H of
                 the features into pinned host memory, every step inside the timed region
 * ``roofline``  algorithmic HBM bytes of the dominant kernel / its CUDA-event duration (events are
                 recorded inside the library on the launching stream) against MEASURED_PEAKS.json.
-                On one stream the step's three kernels are chained by programmatic dependent launch,
-                which an event between two kernels would undo; the events are therefore recorded in a
-                separate single-stream region of the same ``steps`` steps (the kernel timed alone), and
-                that region's own (slower) step time is reported next to them; ``kernel_ms_pipelined``
-                is the same kernel inside the pipelined region
+                The step's three kernels are chained by programmatic dependent launch, which an
+                event between two kernels would undo; the events are therefore recorded in a second
+                region of the same ``steps`` steps right after the timed one, and that region's own
+                (slower) step time is reported next to them
 * ``roofline_fp32``  the same kernel against the FP32 pipe, from the ncu counters of THIS build
                 (profiles/fbank_ncu_metrics.json, keyed by a hash of the kernel sources; null when
                 the committed capture belongs to another build)
@@ -75,9 +69,6 @@ def parse_args():
                     help="BASELINE.json config; cfg2 is the headline, the others are extra measurement rows")
     ap.add_argument("--sweep-hours", type=float, default=1000.0, help="cfg5: corpus size in audio-hours")
     ap.add_argument("--rotate", type=int, default=4, help="distinct synthetic batches generated per rank")
-    ap.add_argument("--streams", type=int, default=4,
-                    help="streams consecutive steps alternate between (utterance CMVN; must divide --rotate; 1 = one "
-                         "stream, the kernels of a step back to back)")
     ap.add_argument("--working-set-gb", type=float, default=4.2,
                     help="device buffers cycled through between timed steps (inputs + outputs), >> L2")
     ap.add_argument("--cfg5-leg-hours", type=float, default=48.0,
@@ -426,34 +417,8 @@ def run_b200(args):
     torch.cuda.synchronize()
     working_set = sum(t.numel() for t in pcm_dev) + 4 * sum(o.numel() for o in outs)
 
-    # Pipelined plans (--streams S > 1, utterance CMVN only): consecutive steps alternate between S streams —
-    # plan k always on stream k % S — so that the statistics and CMVN kernels of one step (a pure HBM stream)
-    # run on the same SMs, at the same time, as the fbank kernel of the next step (FP32 / shared-memory bound,
-    # HBM 90 % idle) instead of queueing behind it.  Every step still runs all three kernels on its own
-    # buffers; the timed region waits for every stream.  --streams 1 = one stream, kernels back to back.
-    S = args.streams if (wl["cmvn"] == "utterance" and R % max(args.streams, 1) == 0) else 1
-    streams = [torch.cuda.Stream(dev) for _ in range(S)] if S > 1 else []
-    main_stream = torch.cuda.current_stream(dev)
-
-    def set_pipelined(on):
-        for p in plans:
-            p.set_pipelined(on)
-
-    def step(i, pipelined=True):
-        k = i % n_buf % R
-        if S > 1 and pipelined:
-            with torch.cuda.stream(streams[k % S]):
-                plans[k].execute(pcm_dev[i % n_buf], outs[i % n_buf])
-        else:
-            plans[k].execute(pcm_dev[i % n_buf], outs[i % n_buf])
-
-    def fork(ev):  # the side streams start after `ev` (recorded on the main stream)
-        for s_ in streams:
-            s_.wait_event(ev)
-
-    def join():    # the main stream waits for everything the side streams were given
-        for s_ in streams:
-            main_stream.wait_stream(s_)
+    def step(i):
+        plans[i % n_buf % R].execute(pcm_dev[i % n_buf], outs[i % n_buf])
 
     def barrier():
         torch.cuda.synchronize()
@@ -462,58 +427,38 @@ def run_b200(args):
             torch.cuda.synchronize()
 
     # ---- device-resident timing ------------------------------------------------------------------
-    set_pipelined(S > 1)
     for i in range(max(args.warmup, 3)):
         step(i)
     clocks = ClockSampler(local_rank)
     barrier()
     clocks.start()
     # (A) the timed region of `value`: exactly `steps` steps, nothing but the product's launches on the
-    # streams.
+    # stream.  The three kernels of a step are chained by programmatic dependent launch; an event
+    # recorded between two kernels would serialise them again, so the per-kernel events of the roofline
+    # line are taken in a second, identical region (B) right after, whose own step time is reported too.
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    fork(ev0)
-    t_host0 = time.perf_counter()
     for i in range(args.steps):
         step(i)
-    host_launch_ms = (time.perf_counter() - t_host0) * 1e3
-    join()
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
-    # (A') the same steps on ONE stream with plans that are not pipelined: the three kernels of a step back to
-    # back, chained by programmatic dependent launch (what a single call costs; the ncu launch list of this
-    # command serialises kernels like this region does)
-    ms_single = ms_total
-    if S > 1:
-        set_pipelined(False)
-        for i in range(3):
-            step(i, pipelined=False)
-        barrier()
-        ev6, ev7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev6.record()
-        for i in range(args.steps):
-            step(i, pipelined=False)
-        ev7.record()
-        barrier()
-        ms_single = ev6.elapsed_time(ev7)
-    # (B) single-stream steps again with CUDA events around the fbank kernel (recorded by the library on the
-    # launching stream): the kernel timed alone.  An event recorded between two kernels serialises what the
-    # programmatic dependent launch overlaps, so this region's own step time is reported too.
+    # (B) same steps again with CUDA events around the fbank kernel (recorded by the library on the
+    # launching stream)
     for p in plans:
         p.enable_profiling((args.steps + R - 1) // R + 1)
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2.record()
     for i in range(args.steps):
-        step(i, pipelined=False)
+        step(i)
     ev3.record()
     barrier()
-    ms_total_events = ev2.elapsed_time(ev3)
-    kt = np.concatenate([p.kernel_times_ms((args.steps + R - 1) // R + 1) for p in plans])
-    kernel_ms = float(kt.mean())
     clk = clocks.stop()
+    ms_total_events = ev2.elapsed_time(ev3)
     hours_done = sum(hours_per_step[i % n_buf % R] for i in range(args.steps))
     frames_done = sum(frames_per_step[i % n_buf % R] for i in range(args.steps))
+    kt = np.concatenate([p.kernel_times_ms((args.steps + R - 1) // R + 1) for p in plans])
+    kernel_ms = float(kt.mean())
     for p in plans:
         p.enable_profiling(0)
     # (C) a longer region (>= 50 ms of device time, same loop) — the driver's --steps 20 region is ~4 ms,
@@ -521,13 +466,10 @@ def run_b200(args):
     long_steps = max(args.steps, int(np.ceil(60.0 / max(ms_total / args.steps, 1e-3))))
     ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev4.record()
-    fork(ev4)
     for i in range(long_steps):
         step(i)
-    join()
     ev5.record()
     barrier()
-    set_pipelined(False)  # the end-to-end leg below drives the plans through HostPipeline (its own streams)
     ms_long = ev4.elapsed_time(ev5)
     hours_long = sum(hours_per_step[i % n_buf % R] for i in range(long_steps))
 
@@ -598,13 +540,6 @@ def run_b200(args):
                 "audio_hours_per_step_per_gpu": float(np.mean(hours_per_step)),
                 "pcm": "resident in HBM", "cmvn": wl["cmvn"] + " (norm_means, norm_vars, before)",
                 "cmvn_path": "fbank epilogue" if wl["cmvn"] == "global" else "fbank+stats, finalize, apply kernels",
-                "streams": S,
-                "pipelining": ("consecutive steps alternate between %d streams (plan k on stream k %% %d, pipelined "
-                               "plans): finalize / apply of one step run on the same SMs as the fbank kernel of "
-                               "the next; every step runs all its kernels on its own buffers" % (S, S))
-                if S > 1 else "one stream, the kernels of a step back to back",
-                "ms_per_step_single_stream": ms_single / args.steps,
-                "host_launch_ms_per_step": host_launch_ms / args.steps,
                 "l2": f"every step uses its own input and output buffers out of a ring of {n_buf} "
                       f"({working_set / 1e9:.2f} GB of inputs+outputs per GPU, >> the 126 MB L2; {R} distinct "
                       "synthetic batches replicated into distinct device buffers)",
@@ -627,11 +562,9 @@ def run_b200(args):
                 "ms_per_step_with_kernel_events": ms_total_events / args.steps,
                 "working_set_bytes": int(working_set),
                 "how": "kernel_ms = mean of CUDA-event pairs recorded by the library around every fbank "
-                       "launch on the launching stream, in a second region of the same `steps` steps on ONE "
-                       "stream right after the timed one: the kernel timed alone, and kernel_share_of_step is "
-                       "its share of THAT region's step (comparable with the ncu launch list, which serialises "
-                       "kernels; events between kernels defeat the programmatic dependent launch, so that "
-                       "region's steps are slower than ms_per_step_single_stream).",
+                       "launch on the launching stream, in a second region of the same `steps` steps right "
+                       "after the timed one (events between kernels defeat the programmatic dependent "
+                       "launch that chains the step's three kernels, so that region's steps are slower)",
             },
             "roofline_fp32": fp32_roofline(metrics, metrics_src, frames_launch, kernel_ms, sm_mhz, n_sm),
             "clocks": clk,

@@ -158,14 +158,8 @@ int js2t_features_execute(js2t_plan* plan, const float* feats_dev, float* out_de
 int js2t_plan_enable_profiling(js2t_plan* plan, int n_slots);
 int js2t_plan_kernel_times_ms(js2t_plan* plan, float* ms_out, int n, int* n_written);
 
-/* Plan options.  "pipelined" = 1: the caller alternates consecutive batches between two or more streams
- * (each plan stays on its stream).  The small kernels of one batch (statistics, CMVN + SpecAugment pass) then
- * run on the same SMs, at the same time, as the fbank kernel of the next batch instead of queueing behind it:
- * they are launched in the shape that fits next to that kernel's two resident CTAs and without programmatic
- * dependent launch.  Results are identical; a plan used on one stream only should leave it at 0.
- * Tuning switches: "max_ctas" caps the persistent grid, "side_ctas" / "side_limit" the launched / resident
- * CTAs per SM of the pipelined CMVN pass, "debug_times" records per-tile time stamps, "debug_skip" skips
- * kernel phases in -DJS2T_DBG=1 builds.  Unknown names are an error. */
+/* Tuning switches: "max_ctas" caps the persistent grid, "debug_times" records per-tile time stamps,
+ * "debug_skip" skips kernel phases in -DJS2T_DBG=1 builds.  Unknown names are an error. */
 int js2t_plan_set_option(js2t_plan* plan, const char* name, int value);
 /* With option "debug_times" = 1: per-tile %globaltimer stamps [n_tiles][4] (tile start, stored,
  * published, normalised-older-tile) of the last execute, copied to host memory (synchronous). */

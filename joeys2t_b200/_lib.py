@@ -16,7 +16,7 @@ from pathlib import Path
 CSRC = Path(__file__).resolve().parent / "csrc"
 # JS2T_LIB selects another build of the same library (tuning A/B runs: tools/build_variant.py)
 LIB_PATH = Path(os.environ["JS2T_LIB"]).resolve() if os.environ.get("JS2T_LIB") else CSRC / "libjoeys2t_b200.so"
-SOURCES = ["fbank_kernels.cu", "side_kernels.cu", "ingest_kernels.cu", "capi.cu"]
+SOURCES = ["fbank_kernels.cu", "ingest_kernels.cu", "capi.cu"]
 HEADERS = ["js2t_internal.h", "mel_structure.inc", "../../include/joeys2t_b200.h"]
 
 # status codes (include/joeys2t_b200.h)
@@ -61,7 +61,7 @@ def kernel_source_sha16() -> str:
     DRAM traffic) are only attached to a bench line when they belong to the build being measured."""
     import hashlib
     h = hashlib.sha256()
-    for f in ("fbank_kernels.cu", "side_kernels.cu", "js2t_internal.h", "mel_structure.inc"):  # device code of the hot path
+    for f in ("fbank_kernels.cu", "js2t_internal.h", "mel_structure.inc"):  # device code of the hot path
         h.update((CSRC / f).resolve().read_bytes())
     return h.hexdigest()[:16]
 

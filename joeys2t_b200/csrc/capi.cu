@@ -71,14 +71,6 @@ struct js2t_ctx {
   // upload and every execute stream waits for it, so the upload is formally ordered before the kernels
   // on whatever stream the caller launches them and plan creation never synchronises the device
   cudaStream_t upload_stream = nullptr;
-  // Pipelined plans: the fbank kernels of consecutive batches come from different streams, but they must run
-  // ONE AFTER THE OTHER — each fills the GPU with its persistent grid, and two of them interleaved bunch the
-  // pipeline up (their small kernels then pile up next to the following fbank kernel).  Every pipelined fbank
-  // launch waits for the event recorded behind the previous one (ring of events, guarded by chain_mu).
-  std::mutex chain_mu;
-  std::vector<cudaEvent_t> chain_ev;
-  size_t chain_next = 0;
-  cudaEvent_t chain_last = nullptr;
   // Device-buffer pool for plan workspaces: the per-item / per-batch callers of the reference API create
   // and destroy one plan per call, and cudaMalloc + cudaFree were a third of such a call.
   std::mutex pool_mu;
@@ -89,7 +81,6 @@ struct js2t_ctx {
 namespace {
 
 constexpr size_t kPoolMaxEntries = 16;
-constexpr int kSideOccInts = 256;  // >= SMs of any device (B200: 148)
 constexpr size_t kPoolMaxBytes = size_t(1) << 30;
 
 // smallest idle buffer that fits without wasting more than 4x, else a fresh allocation (64 KB granules)
@@ -161,12 +152,6 @@ struct js2t_plan {
   bool has_masks = false, global_stats_set = false, stats_valid = false;
   bool feature_input = false;  // rows of 80 floats instead of PCM (js2t_plan_create_features)
   int grid_limit = 0;          // tuning only: option "max_ctas"
-  // option "pipelined": consecutive batches alternate between streams, so that finalize / apply of one batch
-  // run on the same SMs as the fbank kernel of the next (side_kernels.cu): no programmatic dependent launch,
-  // the small finalize shape, the persistent warp-per-tile apply kernel with one resident CTA per SM
-  int pipelined = 0;
-  int side_ctas = 0;           // tuning only, option "side_ctas": CTAs launched per SM of that kernel (0 = default)
-  int side_limit = 1;          // tuning only, option "side_limit": resident CTAs of that kernel per SM (0 = no limit)
   int dbg_skip = 0;            // tuning only: phases of the fbank kernel to skip (results are wrong)
   unsigned long long* d_dbg = nullptr;  // [n_tiles][4] debug time stamps (option "debug_times")
   // optional instrumentation: CUDA events around the fbank kernel of each execute (ring of slots)
@@ -244,8 +229,6 @@ int js2t_ctx_destroy(js2t_ctx* ctx) {
     cudaStreamDestroy(ctx->upload_stream);
   }
   if (ctx->d_tables) cudaFree(ctx->d_tables);
-  for (cudaEvent_t ev : ctx->chain_ev)
-    if (ev) cudaEventDestroy(ev);
   for (auto& b : ctx->pool) cudaFree(b.second);
   delete ctx;
   return JS2T_OK;
@@ -438,7 +421,7 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
   const size_t o_mv = carve(sizeof(float) * n_utts);
   const size_t o_g = carve(sizeof(float) * 2 * kMel);
   const size_t o_ustats = carve(sizeof(double) * kStatsPerTile * n_utts);
-  const size_t o_sched = carve(sizeof(int) * (4 + kSideOccInts));  // fbank kernel [2] | side kernel [2] | its CTAs per SM
+  const size_t o_sched = carve(sizeof(int) * 2);
   const size_t o_row0 = carve(sizeof(long long) * n_utts);
   DeviceGuard guard(ctx->device);
   cudaError_t e = guard.err;
@@ -472,7 +455,7 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
   // upload_stream in front of ready_ev, which every execute stream waits for (plan_begin).
   e = cudaEventCreateWithFlags(&p->ready_ev, cudaEventDisableTiming);
   cudaStream_t us = ctx->upload_stream;
-  if (e == cudaSuccess) e = cudaMemsetAsync(p->d_sched, 0, sizeof(int) * (4 + kSideOccInts), us);
+  if (e == cudaSuccess) e = cudaMemsetAsync(p->d_sched, 0, sizeof(int) * 2, us);
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(p->d_utts, p->h_utts.data(), sizeof(UttDesc) * n_utts, cudaMemcpyHostToDevice, us);
   if (e == cudaSuccess)
@@ -638,12 +621,6 @@ static ApplyLaunch make_apply(const js2t_plan* plan, float* out_dev, bool shared
   a.cmvn_after = (plan->cmvn_mode != JS2T_CMVN_NONE && !plan->before) ? 1 : 0;
   a.pad_tmax = plan->pad_tmax;
   a.pad_value = plan->pad_value;
-  a.pdl = plan->pipelined ? 0 : 1;
-  a.variant = plan->pipelined ? 2 : 0;
-  a.side_ctas_per_sm = plan->side_ctas;
-  a.side_sched = plan->d_sched + 2;
-  a.side_occ = plan->d_sched + 4;
-  a.side_limit = plan->side_limit;
   return a;
 }
 
@@ -669,8 +646,6 @@ static FinalizeLaunch make_finalize(const js2t_plan* plan, const float* raw, boo
   z.istd = plan->d_istd;
   z.mask_value = plan->d_mask_value;
   z.stats_out = plan->d_utt_stats;
-  z.pdl = plan->pipelined ? 0 : 1;
-  z.small = plan->pipelined ? 1 : 0;
   return z;
 }
 
@@ -707,38 +682,19 @@ static int run_pipeline(js2t_plan* plan, const void* in_dev, float* out_dev, cud
   f.dither = from_pcm ? plan->dither : nullptr;
   f.dither_row0 = plan->d_frame_row0;
   f.dbg_skip = plan->dbg_skip;
-  f.pdl = plan->pipelined ? 0 : 1;
-  f.co_resident = plan->pipelined;
   f.grid_limit = plan->grid_limit;
   f.dbg_times = plan->d_dbg;
 
   // the dominant kernel, optionally bracketed by profiling events on the launching stream
   auto launch_main = [&](const FbankLaunch& fl) -> cudaError_t {
-    js2t_ctx* cx = plan->ctx;
-    std::unique_lock<std::mutex> chain_lk(cx->chain_mu, std::defer_lock);
-    if (plan->pipelined && from_pcm) {  // fbank kernels of pipelined plans run one after the other (js2t_ctx)
-      chain_lk.lock();
-      if (cx->chain_ev.empty()) {
-        cx->chain_ev.resize(16, nullptr);
-        for (auto& ev : cx->chain_ev)
-          if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return cudaGetLastError();
-      }
-      if (cx->chain_last != nullptr) {
-        cudaError_t we = cudaStreamWaitEvent(stream, cx->chain_last, 0);
-        if (we != cudaSuccess) return we;
-      }
-    }
     const size_t slots = plan->prof_ev.size() / 2;
     const size_t slot = slots ? (size_t)(plan->prof_calls % (long long)slots) : 0;
     if (slots) cudaEventRecord(plan->prof_ev[2 * slot], stream);
-    FbankLaunch fl2 = fl;
-    if (chain_lk.owns_lock()) fl2.started = cx->chain_ev[cx->chain_next % cx->chain_ev.size()];
-    cudaError_t e = from_pcm ? launch_fbank(fl2, stream) : launch_features(fl2, stream);
+    cudaError_t e = from_pcm ? launch_fbank(fl, stream) : launch_features(fl, stream);
     if (slots) {
       cudaEventRecord(plan->prof_ev[2 * slot + 1], stream);
       plan->prof_calls++;
     }
-    if (chain_lk.owns_lock() && e == cudaSuccess) cx->chain_last = cx->chain_ev[cx->chain_next++ % cx->chain_ev.size()];
     return e;
   };
   // (1) nothing data-dependent after the log-mel: one kernel, one pass over HBM
@@ -772,9 +728,9 @@ static int run_pipeline(js2t_plan* plan, const void* in_dev, float* out_dev, cud
   JS2T_CUDA(launch_main(f));
   const bool shared = (mode == JS2T_CMVN_GLOBAL);
   FinalizeLaunch z = make_finalize(plan, out_dev, shared);
-  if (!(plan->dbg_skip & 0x200)) JS2T_CUDA(launch_finalize(z, stream));  // (timing probes: 0x100 no apply, 0x200 no finalize)
+  JS2T_CUDA(launch_finalize(z, stream));
   plan->stats_valid = true;
-  if (mode != JS2T_CMVN_STATS_ONLY && !(plan->dbg_skip & 0x100)) {
+  if (mode != JS2T_CMVN_STATS_ONLY) {
     ApplyLaunch a = make_apply(plan, out_dev, shared);
     JS2T_CUDA(launch_apply(a, stream));
   }
@@ -823,18 +779,6 @@ int js2t_plan_set_option(js2t_plan* plan, const char* name, int value) {
   if (plan == nullptr || name == nullptr) return fail(JS2T_ERR_INVALID, "NULL argument");
   if (strcmp(name, "max_ctas") == 0) {
     plan->grid_limit = value;
-    return JS2T_OK;
-  }
-  if (strcmp(name, "pipelined") == 0) {
-    plan->pipelined = value ? 1 : 0;
-    return JS2T_OK;
-  }
-  if (strcmp(name, "side_ctas") == 0) {
-    plan->side_ctas = value;
-    return JS2T_OK;
-  }
-  if (strcmp(name, "side_limit") == 0) {
-    plan->side_limit = value;
     return JS2T_OK;
   }
   if (strcmp(name, "debug_skip") == 0) {

@@ -526,15 +526,15 @@ constexpr int kMaxEpilogueMasks = 16;
 // host-drawn noise (sum T, 400) is added to every frame's samples before DC removal.  The two frames of a
 // pair then no longer share their samples, so this variant keeps one set of d values per frame; it is
 // slower and not on the benchmarked path.
-// The kernel exists in two register allocations (launch bounds and __maxnreg__ exclude each other):
-//   fbank_tile_kernel      128 registers per thread: two resident CTAs use the whole register file
-//   fbank_tile_kernel_co   112 registers per thread: two resident CTAs leave 2 048 registers per scheduler
-//                          free, which is what the finalize / apply kernels of the PREVIOUS batch need to run
-//                          on the same SMs at the same time (pipelined plans, side_kernels.cu).  178.2 ->
-//                          179.3 us per config-2 launch, no spills (profiles/r2_corun_ab.txt; 120 registers:
-//                          183.3, 104: 186.7, 96: 187.9 with spills).
-template <int kMode, bool kDither>
-__device__ __forceinline__ void fbank_tile_body(const FbankLaunch& p) {
+// -DJS2T_FBANK_MAXNREG=n (timing probes): an explicit register cap instead of the launch bounds (the two exclude
+// each other) — profiles/r2_corun_ab.txt section 2
+#if defined(JS2T_FBANK_MAXNREG)
+#define JS2T_FBANK_BOUNDS __maxnreg__(JS2T_FBANK_MAXNREG)
+#else
+#define JS2T_FBANK_BOUNDS __launch_bounds__(kThreads, JS2T_MIN_CTAS)
+#endif
+template <int kMode, bool kDither = false>
+__global__ void JS2T_FBANK_BOUNDS fbank_tile_kernel(const FbankLaunch p) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* sWin = reinterpret_cast<float*>(smem + kOffWin);
   float2* sTw256 = reinterpret_cast<float2*>(smem + kOffTw256);
@@ -1089,18 +1089,6 @@ __device__ __forceinline__ void fbank_tile_body(const FbankLaunch& p) {
   }
 }
 
-template <int kMode, bool kDither = false>
-__global__ void __launch_bounds__(kThreads, JS2T_MIN_CTAS) fbank_tile_kernel(const FbankLaunch p) {
-  fbank_tile_body<kMode, kDither>(p);
-}
-#ifndef JS2T_FBANK_CO_REGS
-#define JS2T_FBANK_CO_REGS 112
-#endif
-template <int kMode>
-__global__ void __maxnreg__(JS2T_FBANK_CO_REGS) fbank_tile_kernel_co(const FbankLaunch p) {
-  fbank_tile_body<kMode, false>(p);
-}
-
 // =====================================================================================================
 //  Kernel A': pre-extracted features (the reference's .npy / npy-in-zip branch,
 //  joeynmt/helpers_for_audio.py:100-127) -> same raw layout + per-tile statistics, so that CMVN and
@@ -1134,12 +1122,9 @@ __global__ void __launch_bounds__(kThreads) feature_tile_kernel(const FbankLaunc
 //  Kernel F: per-utterance statistics -> mean / inverse std / SpecAugment fill value
 //  (joeynmt/data_augmentation.py:96-109 CMVN; :43-46 mask value; tokenizers.py:488-493 order)
 // =====================================================================================================
-// Two shapes: <4, 640> when the kernel has the GPU to itself (four threads per statistics column), and
-// <1, 128> for pipelined plans, where it runs NEXT TO the fbank kernel of the following batch and has to fit
-// into the 2 048 registers per scheduler that kernel's two resident CTAs leave free (one warp per scheduler).
-template <int kFinalizeParts, int kFinalizeThreads>
+constexpr int kFinalizeParts = 4;
+constexpr int kFinalizeThreads = kFinalizeParts * kStatsPerTile;  // 640
 __global__ void __launch_bounds__(kFinalizeThreads) finalize_utt_kernel(const FinalizeLaunch p) {
-  static_assert(kFinalizeThreads >= kMel, "one thread per mel bin after the column sums");
   const int u = blockIdx.x;
   const int b = threadIdx.x;  // mel bin (threads >= 80 only help with the column sums)
   pdl_launch();
@@ -1152,28 +1137,21 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_utt_kernel(const Fi
   __shared__ double s_col[kStatsPerTile];
   __shared__ float s_mv;
 
-  // kFinalizeParts threads per statistics column (sums and sums of squares side by side), each over a
-  // fixed contiguous part of the utterance's tiles in tile order, combined in a fixed order:
-  // deterministic, and the kernel (pure L2 latency) has that many times the loads in flight
-  for (int w = b; w < kFinalizeParts * kStatsPerTile; w += kFinalizeThreads) {
-    const int col = w % kStatsPerTile, part = w / kStatsPerTile;
+  {
+    // four threads per statistics column (sums and sums of squares side by side), each over a fixed
+    // contiguous quarter of the utterance's tiles in tile order, combined in a fixed order:
+    // deterministic, and the kernel (pure L2 latency) has four times the loads in flight
+    const int col = b % kStatsPerTile, part = b / kStatsPerTile;
     const int per = (n_tiles + kFinalizeParts - 1) / kFinalizeParts;
     const int lo = min(part * per, n_tiles), hi = min(lo + per, n_tiles);
     const float* ts = p.tile_stats + ((long long)ud.tile_start + lo) * kStatsPerTile;
     s_part[part][col] = sum_tile_column(ts + col, hi - lo);
   }
   __syncthreads();
-  for (int c = b; c < kStatsPerTile; c += kFinalizeThreads) {
-    double acc;
-    if constexpr (kFinalizeParts == 4) {
-      acc = (s_part[0][c] + s_part[1][c]) + (s_part[2][c] + s_part[3][c]);
-    } else {
-      acc = s_part[0][c];
-#pragma unroll
-      for (int q = 1; q < kFinalizeParts; ++q) acc += s_part[q][c];
-    }
-    s_col[c] = acc;
-    if (p.stats_out != nullptr) p.stats_out[(long long)u * kStatsPerTile + c] = acc;
+  if (b < kStatsPerTile) {
+    const double acc = (s_part[0][b] + s_part[1][b]) + (s_part[2][b] + s_part[3][b]);
+    s_col[b] = acc;
+    if (p.stats_out != nullptr) p.stats_out[(long long)u * kStatsPerTile + b] = acc;
   }
   __syncthreads();
   double S = 0.0, Q = 0.0;
@@ -1438,16 +1416,6 @@ int fbank_persistent_grid() {
     cudaFuncSetAttribute(fbank_tile_kernel<kModeRaw>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     cudaFuncSetAttribute(fbank_tile_kernel<kModeNormKnown>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     cudaFuncSetAttribute(fbank_tile_kernel<kModeRaw, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    cudaFuncSetAttribute(fbank_tile_kernel_co<kModeRaw>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    cudaFuncSetAttribute(fbank_tile_kernel_co<kModeNormKnown>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    // the kernels that may share an SM (pipelined plans: finalize / apply of one batch next to the fbank kernel
-    // of the next) must agree on the shared-memory carve-out: an SM only runs CTAs of kernels whose carve-out
-    // matches its current configuration
-#if JS2T_FBANK_CARVEOUT >= 0
-    cudaFuncSetAttribute(fbank_tile_kernel_co<kModeRaw>, cudaFuncAttributePreferredSharedMemoryCarveout, JS2T_FBANK_CARVEOUT);
-    cudaFuncSetAttribute(fbank_tile_kernel_co<kModeNormKnown>, cudaFuncAttributePreferredSharedMemoryCarveout, JS2T_FBANK_CARVEOUT);
-#endif
-    cudaFuncSetAttribute(finalize_utt_kernel<1, 128>, cudaFuncAttributePreferredSharedMemoryCarveout, JS2T_SIDE_CARVEOUT);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fbank_tile_kernel<kModeRaw>, kThreads, kSmemBytes);
     if (occ < 1) occ = 1;
     g_fbank_grid = occ * n_sm;  // every CTA resident at once: one wave, persistent
@@ -1456,29 +1424,19 @@ int fbank_persistent_grid() {
 }
 
 // launch with programmatic stream serialization (see pdl_wait / pdl_launch)
-// `started` (optional): a programmatic event that fires once every CTA of the grid has issued
-// griddepcontrol.launch_dependents (the fbank kernel does so on entry), i.e. when the whole persistent grid is
-// resident — what the fbank launch of the NEXT pipelined batch, on another stream, waits for
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(bool pdl, cudaEvent_t started, void (*kernel)(KArgs...), dim3 grid, dim3 block,
-                              size_t smem, cudaStream_t s, Args&&... args) {
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = (JS2T_PDL && pdl) ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = JS2T_PDL ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (started != nullptr) {
-    attr[1].id = cudaLaunchAttributeProgrammaticEvent;
-    attr[1].val.programmaticEvent.event = started;
-    attr[1].val.programmaticEvent.flags = 0;
-    attr[1].val.programmaticEvent.triggerAtBlockStart = 0;
-    cfg.numAttrs = 2;
-  }
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
@@ -1489,33 +1447,26 @@ cudaError_t launch_fbank(const FbankLaunch& p, cudaStream_t s) {
   const int grid = p.n_tiles < full ? p.n_tiles : full;
   if (p.dither != nullptr) {  // compatibility mode: raw epilogue only (capi.cu routes CMVN through the apply kernel)
     if (p.epilogue != kEpiRaw) return cudaErrorInvalidValue;
-    return launch_pdl(p.pdl != 0, nullptr, fbank_tile_kernel<kModeRaw, true>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
-  }
-  if (p.co_resident) {  // pipelined plans: the allocation that leaves room for the previous batch's side kernels
-    if (p.epilogue == kEpiNormKnown)
-      return launch_pdl(p.pdl != 0, p.started, fbank_tile_kernel_co<kModeNormKnown>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
-    return launch_pdl(p.pdl != 0, p.started, fbank_tile_kernel_co<kModeRaw>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
+    return launch_pdl(fbank_tile_kernel<kModeRaw, true>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
   }
   if (p.epilogue == kEpiNormKnown)
-    return launch_pdl(p.pdl != 0, nullptr, fbank_tile_kernel<kModeNormKnown>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
-  return launch_pdl(p.pdl != 0, nullptr, fbank_tile_kernel<kModeRaw>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
+    return launch_pdl(fbank_tile_kernel<kModeNormKnown>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
+  return launch_pdl(fbank_tile_kernel<kModeRaw>, dim3(grid), dim3(kThreads), kSmemBytes, s, p);
 }
 
 cudaError_t launch_features(const FbankLaunch& p, cudaStream_t s) {
   if (p.n_tiles <= 0) return cudaSuccess;
-  return launch_pdl(p.pdl != 0, nullptr, feature_tile_kernel, dim3(p.n_tiles), dim3(kThreads), 0, s, p);
+  return launch_pdl(feature_tile_kernel, dim3(p.n_tiles), dim3(kThreads), 0, s, p);
 }
 
 cudaError_t launch_finalize(const FinalizeLaunch& p, cudaStream_t s) {
   if (p.n_utts <= 0) return cudaSuccess;
-  if (p.small) return launch_pdl(p.pdl != 0, nullptr, finalize_utt_kernel<1, 128>, dim3(p.n_utts), dim3(128), 0, s, p);
-  return launch_pdl(p.pdl != 0, nullptr, finalize_utt_kernel<4, 640>, dim3(p.n_utts), dim3(640), 0, s, p);
+  return launch_pdl(finalize_utt_kernel, dim3(p.n_utts), dim3(kFinalizeThreads), 0, s, p);
 }
 
 cudaError_t launch_apply(const ApplyLaunch& p, cudaStream_t s) {
   if (p.n_tiles <= 0) return cudaSuccess;
-  if (p.variant == 2) return launch_apply_warp(p, s);  // side_kernels.cu
-  return launch_pdl(p.pdl != 0, nullptr, apply_kernel, dim3(p.n_tiles), dim3(kApplyThreads), 0, s, p);
+  return launch_pdl(apply_kernel, dim3(p.n_tiles), dim3(kApplyThreads), 0, s, p);
 }
 
 cudaError_t launch_global_accumulate(const double* utt_stats, const UttDesc* utts, int n_utts,

@@ -77,9 +77,6 @@ struct FbankLaunch {
   // dither_row0[u] = first row of utterance u in that array.  nullptr = off (the reference's dither = 0).
   const float* dither;
   const long long* dither_row0;
-  int pdl;         // 1: launched with programmatic stream serialization (single-stream plans)
-  cudaEvent_t started;  // host side only: programmatic event "the whole grid is resident" (pipelined plans) or nullptr
-  int co_resident; // 1: the 112-register build that leaves room for side kernels on the same SM (pipelined plans)
   int grid_limit;  // tuning only: cap on the persistent grid (0 = all resident CTAs)
   int dbg_skip;  // tuning only: bit0 staging, bit1 FFT phase, bit2 mel, bit3 store, bit4 butterflies, bit5 exchange
   unsigned long long* dbg_times;  // [n_tiles][4] globaltimer stamps (debug / tuning only) or nullptr
@@ -103,8 +100,6 @@ struct FinalizeLaunch {
   float* istd;           // [n_utts][80]
   float* mask_value;     // [n_utts]
   double* stats_out;     // [n_utts][160] raw per-utterance sum | sumsq in fp64, or nullptr
-  int pdl;               // 1: launched with programmatic stream serialization (single-stream plans)
-  int small;             // 1: the 128-thread shape that fits next to the fbank kernel (pipelined plans)
 };
 
 struct ApplyLaunch {
@@ -121,12 +116,6 @@ struct ApplyLaunch {
   int cmvn_after;           // 1: fill first, then normalise (cmvn.before == False)
   int pad_tmax;
   float pad_value;
-  int pdl;               // 1: launched with programmatic stream serialization (single-stream plans)
-  int variant;           // 0: one CTA per tile (apply_kernel); 2: persistent, one warp per tile (apply_warp_kernel)
-  int side_ctas_per_sm;  // variant 2: grid = this many CTAs per SM (0 = default)
-  int* side_sched;       // variant 2: [2] tile claim counter | CTAs that have left (self-resetting)
-  int* side_occ;         // variant 2: [n_sm] CTAs of THIS launch resident per SM (zero between launches)
-  int side_limit;        // variant 2: at most this many per SM (0 = no limit)
 };
 
 cudaError_t upload_mel_weights(const float* wu256, const float* wd256, cudaStream_t s);
@@ -136,7 +125,6 @@ cudaError_t launch_fbank(const FbankLaunch& p, cudaStream_t s);
 cudaError_t launch_features(const FbankLaunch& p, cudaStream_t s);  // p.pcm = feature rows
 cudaError_t launch_finalize(const FinalizeLaunch& p, cudaStream_t s);
 cudaError_t launch_apply(const ApplyLaunch& p, cudaStream_t s);
-cudaError_t launch_apply_warp(const ApplyLaunch& p, cudaStream_t s);  // side_kernels.cu
 // accum[0..79] += sum, accum[80..159] += sumsq, accum[160] += frames  (fixed order => deterministic)
 cudaError_t launch_global_accumulate(const double* utt_stats, const UttDesc* utts, int n_utts,
                                      double* accum, cudaStream_t s);
@@ -147,14 +135,6 @@ cudaError_t launch_fill_value(float* dst, int n, float value, cudaStream_t s);
 // 48 kHz -> 16 kHz ingest (scripts/gradio_demo.py:35-45); ws = one int of device scratch
 cudaError_t launch_reformat_48k_to_16k(const void* src, int is_f32, long long n_samples, short* dst, int* ws,
                                        cudaStream_t s);
-// shared-memory carve-out (percent of the maximum) requested for the fbank kernel (-1: the driver's choice)
-// and for the kernels that run next to it
-#ifndef JS2T_FBANK_CARVEOUT
-#define JS2T_FBANK_CARVEOUT -1
-#endif
-#ifndef JS2T_SIDE_CARVEOUT
-#define JS2T_SIDE_CARVEOUT 86
-#endif
 int fbank_smem_bytes();
 int fbank_persistent_grid();  // CTAs of the persistent fbank kernel on the current device
 

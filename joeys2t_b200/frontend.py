@@ -272,12 +272,6 @@ class Plan:
         _lib.check(self._lib.js2t_plan_set_option(self._h, name.encode(), int(value)))
         return self
 
-    def set_pipelined(self, on: bool = True) -> "Plan":
-        """The caller alternates consecutive batches between two or more streams (each plan stays on its
-        stream): the statistics and CMVN / SpecAugment kernels of one batch then run next to the fbank kernel
-        of the next batch on the same SMs (``js2t_plan_set_option(plan, "pipelined", 1)``).  Same results."""
-        return self.set_option("pipelined", int(on))
-
     def debug_times(self) -> np.ndarray:
         """(n_tiles, 4) uint64 %globaltimer stamps of the last execute (option "debug_times")."""
         n_tiles = int(np.sum((np.maximum(self.n_frames, 1) + 31) // 32)) if self.layout == "ragged" \

@@ -301,62 +301,3 @@ def test_dither_compat_mode_vs_torchaudio(fe, fixtures_pcm):
     # zero noise == dither off, bit for bit
     zero, _ = fe.fbank_cmvn_specaug_ragged(waves, dither_noise=np.zeros_like(noise))
     assert np.array_equal(zero.cpu().numpy(), plain)
-
-
-# ---- pipelined plans: finalize / apply of one batch next to the fbank kernel of the next ---------------
-@pytest.mark.gpu
-@pytest.mark.parametrize("layout", ["ragged", "padded"])
-@pytest.mark.parametrize("before", [True, False])
-def test_pipelined_plans_on_two_streams_are_bit_identical(layout, before):
-    """``js2t_plan_set_option(plan, "pipelined", 1)`` changes which kernels run the CMVN / SpecAugment pass
-    (128-thread finalize, persistent warp-per-tile apply with a residency gate, no programmatic dependent
-    launch) and lets them overlap the next batch's fbank kernel; the results must not change by a bit.
-    Reference for the values themselves: the non-pipelined path, which the tests above pin to the oracle
-    (joeynmt/data_augmentation.py:96-109, :38-73; helpers_for_audio.py:130-170)."""
-    import torch
-    from joeys2t_b200 import frontend
-
-    rng = np.random.RandomState(7)
-    batches = []
-    for b in range(4):
-        # ragged lengths incl. a one-frame utterance, tile-boundary lengths and mixed int16 / float32 PCM
-        lens = [400, 400 + 160 * 31, 400 + 160 * 32, 5521, 16000 * 3 + 17, 16000 * 7, 16000 * 11 + 3][b % 3:]
-        waves = []
-        for i, n in enumerate(lens):
-            w = (np.cumsum(rng.randint(-400, 401, n)) % 20001 - 10000).astype(np.int16)  # any signal will do
-            waves.append(w.astype(np.float32) / np.float32(32768.0) if (i + b) % 3 == 0 else w)
-        packed = frontend.PackedPCM(waves)
-        kw = dict(layout=layout)
-        if layout == "padded":
-            kw["pad_tmax"] = int(max(1 + (len(w) - 400) // 160 for w in waves)) + 5
-        n_f, n_t = 2, 3
-        table = np.zeros((len(waves), n_f + n_t, 2), np.int32)
-        for u, w in enumerate(waves):
-            T = 1 + (len(w) - 400) // 160
-            table[u, :n_f, 0] = rng.randint(0, 70, n_f)
-            table[u, :n_f, 1] = rng.randint(0, 12, n_f)
-            table[u, n_f:, 0] = rng.randint(0, max(T, 1), n_t)
-            table[u, n_f:, 1] = rng.randint(0, 40, n_t)
-        outs = []
-        for pipelined in (False, True):
-            plan = frontend.Plan(packed.n_samples, packed.byte_off, packed.is_f32, **kw)
-            plan.set_cmvn("utterance", before=before)
-            plan.set_masks(table, n_f, n_t)
-            plan.set_pipelined(pipelined)
-            outs.append((plan, packed.to_device(), plan.empty_output()))
-        batches.append(outs)
-    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
-    torch.cuda.synchronize()
-    for rep in range(3):  # several rounds: the kernels of consecutive batches really do overlap
-        for b, outs in enumerate(batches):
-            plan, dev, out = outs[1]
-            with torch.cuda.stream(streams[b % 2]):
-                plan.execute(dev, out)
-    for b, outs in enumerate(batches):
-        plan, dev, out = outs[0]
-        plan.execute(dev, out)
-    torch.cuda.synchronize()
-    for b, outs in enumerate(batches):
-        ref, got = outs[0][2].cpu().numpy(), outs[1][2].cpu().numpy()
-        assert np.isfinite(ref).all()
-        assert np.array_equal(ref.view(np.uint32), got.view(np.uint32)), f"batch {b}: pipelined result differs"
