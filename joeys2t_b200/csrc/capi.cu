@@ -407,8 +407,58 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
   // partial last tile of every utterance, then pure padding — go to the end, where they shorten the
   // tail in which CTAs run out of work (full tiles keep their utterance order).  Where a tile's rows
   // and statistics land does not depend on this order (out_row0, stats_slot).
-  std::stable_sort(tiles.begin(), tiles.end(),
-                   [](const TileDesc& a, const TileDesc& b) { return a.nf > b.nf; });
+  const char* probe_order = getenv("JS2T_PROBE_TILE_ORDER");
+  if (probe_order != nullptr && atoi(probe_order) > 0 && !feat) {
+    // TIMING PROBE ONLY (tools/cluster_probe.py, -DJS2T_PROBE_STATIC=1 builds, profiles/r2_cluster_probe.txt): the
+    // tile array as a STATIC schedule of "one cluster of cs CTAs per utterance" — position i * G + b holds the i-th
+    // tile of CTA b (G = persistent grid): cluster b / cs takes utterances c, c + n_clusters, ...; CTA b % cs of the
+    // cluster takes tiles r, r + cs, ... of each of them; holes are empty tiles.  cs = 1: plain static round-robin
+    // of the processing order below.
+    const int cs = atoi(probe_order);
+    const int G = fbank_persistent_grid();
+    std::vector<TileDesc> sched;
+    if (cs == 1) {
+      std::stable_sort(tiles.begin(), tiles.end(), [](const TileDesc& a, const TileDesc& b) { return a.nf > b.nf; });
+      sched = tiles;
+    } else {
+      const int n_clusters = G / cs;
+      std::vector<std::vector<TileDesc>> seq((size_t)G);
+      const bool barrier_slots = getenv("JS2T_PROBE_CLUSTER_SLOTS") != nullptr;  // every CTA of a cluster takes the same number of slots per utterance
+      for (int u = 0; u < n_utts; ++u) {
+        const int c = u % n_clusters;
+        const int first = p->h_utts[u].tile_start;
+        const int nt = (u + 1 < n_utts ? p->h_utts[u + 1].tile_start : (int)tiles.size()) - first;
+        const int per = (nt + cs - 1) / cs;
+        for (int r = 0; r < cs; ++r) {
+          int got = 0;
+          for (int j = r; j < nt; j += cs, ++got) seq[(size_t)(c * cs + r)].push_back(tiles[(size_t)(first + j)]);
+          if (barrier_slots)
+            for (; got < per; ++got) {
+              TileDesc e = tiles[(size_t)first];
+              e.nf = 0;
+              e.rows = 0;
+              e.stats_slot = (int)tiles.size();  // dummy statistics row (the array below is sized by the schedule)
+              seq[(size_t)(c * cs + r)].push_back(e);
+            }
+        }
+      }
+      size_t L = 0;
+      for (auto& s : seq) L = std::max(L, s.size());
+      TileDesc empty = tiles[0];
+      empty.nf = 0;
+      empty.rows = 0;
+      empty.stats_slot = (int)tiles.size();
+      sched.assign(L * (size_t)G, empty);
+      for (int b = 0; b < G; ++b)
+        for (size_t i = 0; i < seq[(size_t)b].size(); ++i) sched[i * (size_t)G + (size_t)b] = seq[(size_t)b][i];
+      sched.push_back(empty);  // room for the dummy statistics row
+    }
+    tiles.swap(sched);
+    p->n_tiles = (int)tiles.size();
+  } else {
+    std::stable_sort(tiles.begin(), tiles.end(),
+                     [](const TileDesc& a, const TileDesc& b) { return a.nf > b.nf; });
+  }
 
   // one device allocation, carved up
   size_t off = 0;

@@ -590,7 +590,13 @@ __global__ void JS2T_FBANK_BOUNDS fbank_tile_kernel(const FbankLaunch p) {
 #ifndef JS2T_SCHED_PIPE
 #define JS2T_SCHED_PIPE 1
 #endif
-#if JS2T_SCHED_PIPE
+#if defined(JS2T_PROBE_STATIC) && JS2T_PROBE_STATIC
+  // TIMING PROBE ONLY: static schedule — CTA b takes array positions b, b + G, b + 2 G, ... (capi.cu builds the
+  // array for it when JS2T_PROBE_TILE_ORDER is set)
+  int tile = (int)blockIdx.x;
+  int next_tile = tile + (int)gridDim.x;
+  int claim_cur = tile + 2 * (int)gridDim.x, claim_next = 0;
+#elif JS2T_SCHED_PIPE
   if (is_sched) sClaim = atomicAdd(p.sched, 3);
   __syncthreads();
   int tile = sClaim;
@@ -632,7 +638,11 @@ __global__ void JS2T_FBANK_BOUNDS fbank_tile_kernel(const FbankLaunch p) {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"((const char*)src + 16)
                      : "memory");
       }
+#if defined(JS2T_PROBE_STATIC) && JS2T_PROBE_STATIC
+      claim_next = claim_cur + (int)gridDim.x;
+#else
       claim_next = atomicAdd(p.sched, 1);
+#endif
     }
 #else
     if (is_sched) sClaim = atomicAdd(p.sched, 1);  // claim two ahead; consumed at the end of the iteration
