@@ -204,6 +204,55 @@ int js2t_plan_copy_global_stats(const js2t_plan* plan, float* dst_dev, void* str
 int js2t_pack_pcm(int n_utts, const void* const* src, const int64_t* n_bytes, const int64_t* dst_byte_off,
                   void* dst, int64_t dst_capacity, int n_threads);
 
+/* ---- one call per batch, utterances in HOST memory ----------------------------------------------------
+ * What a per-batch caller of the reference's data path needs (collate_fn -> Batch: joeynmt/datasets.py:221-225,
+ * batch.py:114-121; SpeechProcessor per item: tokenizers.py:458-494): n_utts waveforms in host memory in,
+ * features on the device out.  The call gathers the utterances into a pinned staging slot owned by the context
+ * (js2t_pack_pcm's copy pool), lays the batch's descriptors, mask table and global statistics out next to the
+ * PCM, uploads all of it with ONE transfer on `stream` and enqueues the kernels behind it; it returns without
+ * waiting for the device.  The waveform arrays may be reused as soon as the call returns.
+ *   pcm_host[u]   n_samples[u] samples: int16, or float32 in [-1, 1) where is_f32[u] != 0 (is_f32 may be NULL)
+ *   opts          layout / CMVN / SpecAugment of the batch, same meaning as js2t_plan_create, js2t_plan_set_cmvn,
+ *                 js2t_plan_set_global_stats (GLOBAL: both statistics arrays required) and js2t_plan_set_masks
+ *   out_dev       float32 rows of 80 on the device, out_capacity_rows of them: sum of the utterances' frames
+ *                 (ragged) or n_utts * Tmax (padded; Tmax = pad_tmax, or the longest utterance when pad_tmax = 0)
+ *   plan_out      NULL: the context keeps the batch's plan and destroys it once the event behind its last kernel
+ *                 has completed; otherwise the caller owns it (statistics read-back, js2t_plan_destroy)
+ * Errors as the calls it combines (too-short utterance: JS2T_ERR_SHORT_INPUT, ...); nothing is enqueued then. */
+typedef struct js2t_batch_opts {
+  int layout;                  /* JS2T_LAYOUT_RAGGED | JS2T_LAYOUT_PADDED */
+  int pad_tmax;                /* padded layout: rows per utterance, 0 = the longest utterance */
+  float pad_value;             /* padded layout: fill value (the reference pads with float(pad_index) = 1.0) */
+  int cmvn_mode;               /* JS2T_CMVN_NONE | JS2T_CMVN_UTTERANCE | JS2T_CMVN_GLOBAL */
+  int norm_means, norm_vars, before;
+  const double* global_mean80; /* JS2T_CMVN_GLOBAL: mean[80] and 1/std[80] */
+  const double* global_istd80;
+  int n_fmask, n_tmask;        /* SpecAugment: masks per utterance */
+  const int32_t* mask_table;   /* [n_utts][n_fmask + n_tmask][2] = (start, width), frequency masks first; NULL = none */
+  int mask_value_mode;         /* JS2T_MASK_VALUE_MEAN | JS2T_MASK_VALUE_CONST */
+  float mask_value_const;
+  const int32_t* max_frames;   /* [n_utts] truncation (tokenizers.py:480-481), entries <= 0 = none; NULL = none */
+} js2t_batch_opts;
+int js2t_batch_fbank(js2t_ctx* ctx, int n_utts, const void* const* pcm_host, const int64_t* n_samples,
+                     const uint8_t* is_f32, const js2t_batch_opts* opts, float* out_dev, int64_t out_capacity_rows,
+                     void* stream, js2t_plan** plan_out);
+
+/* ---- SpecAugment draws of a whole batch (host code) --------------------------------------------------------
+ * The reference draws its masks per item from the global np.random stream (joeynmt/data_augmentation.py:48-70:
+ * f = randint(0, F), f0 = randint(0, num_freqs - f) per frequency mask, then t = randint(0, min(T_max,
+ * floor(num_frames * p))), t0 = randint(0, num_frames - t) per time mask), and a seeded run must mask the same
+ * cells.  numpy's legacy generator serves randint(0, hi) by masked rejection on the 32-bit outputs of its bit
+ * generator; this function performs the draws of a whole batch, in utterance order, on the caller's generator
+ * (numpy's own: BitGenerator.ctypes.next_uint32 / .state), so values AND stream position are exactly what the
+ * reference's loop gives — 128 Python-level randint calls per 16-utterance batch cost more host time than the
+ * batch's kernels.  time_mask_p < 0 or freq_mask_f > num_freqs etc. are left to the caller's per-item route.
+ *   table_out     int32 [n_utts][freq_mask_n + time_mask_n][2] = (start, width); utterances the reference leaves
+ *                 untouched (no frames) and width-0 masks are all-zero rows */
+typedef uint32_t (*js2t_next_uint32_fn)(void* rng_state);
+int js2t_specaug_replay(js2t_next_uint32_fn next_uint32, void* rng_state, int n_utts, const int32_t* n_frames,
+                        int num_freqs, int freq_mask_n, int freq_mask_f, int time_mask_n, int time_mask_t,
+                        double time_mask_p, int32_t* table_out);
+
 /* ---- PCM ingest: 48 kHz -> 16 kHz -------------------------------------------
  * Replaces scripts/gradio_demo.py:35-45 reformat_freq for sr == 48000:
  *     y = ((y / max(np.max(y), 1)) * 32767).reshape((-1, 3)).mean(axis=1).astype("int16")

@@ -35,8 +35,18 @@ EXPORTED_SYMBOLS = [
     "js2t_plan_set_option", "js2t_plan_debug_times", "js2t_plan_utt_stats", "js2t_plan_copy_utt_stats", "js2t_global_stats_accumulate",
     "js2t_global_stats_allreduce", "js2t_nccl_unique_id", "js2t_nccl_comm_create", "js2t_nccl_comm_destroy",
     "js2t_global_stats_finalize", "js2t_normalize_execute", "js2t_plan_copy_global_stats",
-    "js2t_reformat_48k_to_16k", "js2t_pack_pcm",
+    "js2t_reformat_48k_to_16k", "js2t_pack_pcm", "js2t_batch_fbank", "js2t_specaug_replay",
 ]
+
+
+class BatchOpts(ctypes.Structure):
+    """``js2t_batch_opts`` (include/joeys2t_b200.h)."""
+    _fields_ = [("layout", ctypes.c_int), ("pad_tmax", ctypes.c_int), ("pad_value", ctypes.c_float),
+                ("cmvn_mode", ctypes.c_int), ("norm_means", ctypes.c_int), ("norm_vars", ctypes.c_int),
+                ("before", ctypes.c_int), ("global_mean80", ctypes.c_void_p), ("global_istd80", ctypes.c_void_p),
+                ("n_fmask", ctypes.c_int), ("n_tmask", ctypes.c_int), ("mask_table", ctypes.c_void_p),
+                ("mask_value_mode", ctypes.c_int), ("mask_value_const", ctypes.c_float),
+                ("max_frames", ctypes.c_void_p)]
 
 
 class Js2tError(RuntimeError):
@@ -136,6 +146,8 @@ def _declare(lib):
     lib.js2t_plan_copy_global_stats.argtypes = [vp, vp, vp]
     lib.js2t_reformat_48k_to_16k.argtypes = [vp, vp, i32, i64, vp, vp, vp]
     lib.js2t_pack_pcm.argtypes = [i32, vp, vp, vp, vp, i64, i32]
+    lib.js2t_specaug_replay.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, i32, c.c_double, vp]
+    lib.js2t_batch_fbank.argtypes = [vp, i32, vp, vp, vp, P(BatchOpts), vp, i64, vp, vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is c.c_int and name not in ("js2t_version",):

@@ -134,10 +134,27 @@ class SpeechBatchCollator:
         if src is None:
             raise ValueError(f"every item of the batch {list(indices)} was filtered out")
         # pinned + non-blocking: a pageable host-to-device copy would wait for everything enqueued so far
-        # (the batch's own H2D and kernels) and serialise the caller with the GPU
-        host_len = torch.tensor(lengths, dtype=torch.long).pin_memory()
-        src_length = host_len.to(src.device, non_blocking=True)
+        # (the batch's own H2D and kernels) and serialise the caller with the GPU.  The pinned memory comes
+        # from a small ring owned by the collator (a fresh pin_memory() per batch costs more than the batch's
+        # kernel launches); a ring entry is rewritten only after the copy that read it has completed.
+        host_len, ev = self._length_slot(len(lengths))
+        host_len[:len(lengths)] = torch.as_tensor(lengths, dtype=torch.long)
+        src_length = host_len[:len(lengths)].to(src.device, non_blocking=True)
+        ev.record(torch.cuda.current_stream(src.device))
         return src, src_length, kept
+
+    def _length_slot(self, n: int):
+        ring = self.__dict__.setdefault("_len_ring", [])
+        if len(ring) < 8:
+            ring.append([torch.empty(max(n, 1024), dtype=torch.long).pin_memory(), torch.cuda.Event()])
+            self._len_next = len(ring) - 1
+        else:
+            self._len_next = (self._len_next + 1) % len(ring)
+        slot = ring[self._len_next]
+        slot[1].synchronize()  # (never recorded: returns at once)
+        if slot[0].numel() < n:
+            slot[0] = torch.empty(2 * n, dtype=torch.long).pin_memory()
+        return slot[0], slot[1]
 
 
 def lengths_from_dataset(dataset) -> Tuple[np.ndarray, Optional[np.ndarray]]:

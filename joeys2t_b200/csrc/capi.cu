@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <new>
@@ -76,6 +77,19 @@ struct js2t_ctx {
   std::mutex pool_mu;
   std::vector<std::pair<size_t, void*>> pool;  // (capacity, pointer) of idle buffers
   size_t pool_bytes = 0;
+  // js2t_batch_fbank: pinned staging slots (PCM + descriptors of one batch, uploaded with one transfer; a slot
+  // is free again once the event behind its transfer has completed) and the plans of earlier calls that the
+  // context destroys once the event behind their last kernel has completed
+  struct StagingSlot {
+    char* host = nullptr;
+    size_t cap = 0;
+    cudaEvent_t ev = nullptr;
+    bool in_flight = false;
+  };
+  std::mutex batch_mu;
+  std::vector<StagingSlot> slots;
+  std::vector<std::pair<cudaEvent_t, js2t_plan*>> retired;
+  std::vector<cudaEvent_t> spare_events;
 };
 
 namespace {
@@ -145,6 +159,8 @@ struct js2t_plan {
   int max_utt_tiles = 0;
   int* d_masks = nullptr;
   size_t masks_cap = 0;
+  bool masks_in_ws = false;  // js2t_batch_fbank: the mask table lives in the workspace (uploaded with the batch)
+  const uint8_t* d_pcm = nullptr;  // js2t_batch_fbank: the batch's PCM inside the workspace
   // configuration
   int cmvn_mode = JS2T_CMVN_NONE, norm_means = 1, norm_vars = 1, before = 1;
   int n_fmask = 0, n_tmask = 0, mask_value_mode = JS2T_MASK_VALUE_MEAN;
@@ -228,6 +244,19 @@ int js2t_ctx_destroy(js2t_ctx* ctx) {
     cudaStreamSynchronize(ctx->upload_stream);
     cudaStreamDestroy(ctx->upload_stream);
   }
+  for (auto& r : ctx->retired) {  // plans of js2t_batch_fbank calls the context still owns
+    cudaEventSynchronize(r.first);
+    cudaEventDestroy(r.first);
+    js2t_plan_destroy_completed(r.second);
+  }
+  for (cudaEvent_t ev : ctx->spare_events) cudaEventDestroy(ev);
+  for (auto& sl : ctx->slots) {
+    if (sl.ev) {
+      cudaEventSynchronize(sl.ev);
+      cudaEventDestroy(sl.ev);
+    }
+    if (sl.host) cudaFreeHost(sl.host);
+  }
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   for (auto& b : ctx->pool) cudaFree(b.second);
   delete ctx;
@@ -304,10 +333,23 @@ int js2t_ctx_set_tables(js2t_ctx* ctx, const float* window400, const float* mel8
 }
 
 // ---------------------------------------------------------------------------------------------
+// js2t_batch_fbank: everything the device needs from the host for one batch sits at the head of the plan's
+// workspace — descriptors, scheduler counters, global statistics, mask table, PCM — so that ONE transfer from a
+// pinned staging slot uploads it; plan_create_common then only lays the workspace out and hands the descriptors
+// back instead of uploading them itself.
+struct BatchHead {
+  size_t mask_bytes = 0, pcm_bytes = 0;  // in: room to reserve
+  size_t head_bytes = 0;                 // out: workspace bytes [0, head_bytes) = the upload region
+  size_t o_utts = 0, o_tiles = 0, o_row0 = 0, o_sched = 0, o_g = 0, o_masks = 0, o_pcm = 0;
+  std::vector<TileDesc> tiles;
+  std::vector<long long> row0;
+};
+
 // n_frames_in != NULL: feature-input plan (rows of 80 floats, packed back to back)
 static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte_off, const int64_t* n_samples,
                               const uint8_t* is_f32, const int32_t* max_frames, const int32_t* n_frames_in,
-                              int layout, int pad_tmax, float pad_value, js2t_plan** out) {
+                              int layout, int pad_tmax, float pad_value, js2t_plan** out,
+                              BatchHead* head = nullptr) {
   const bool feat = n_frames_in != nullptr;
   if (ctx == nullptr || out == nullptr || (!feat && (pcm_byte_off == nullptr || n_samples == nullptr)))
     return fail(JS2T_ERR_INVALID, "js2t_plan_create: NULL argument");
@@ -465,14 +507,25 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
   auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   const size_t o_utts = carve(sizeof(UttDesc) * n_utts);
   const size_t o_tiles = carve(sizeof(TileDesc) * tiles.size());
+  size_t o_sched = 0, o_row0 = 0, o_g = 0, o_masks = 0, o_pcm = 0;
+  if (head != nullptr) {  // the upload region first (see BatchHead)
+    o_row0 = carve(sizeof(long long) * n_utts);
+    o_sched = carve(sizeof(int) * 2);
+    o_g = carve(sizeof(float) * 2 * kMel);
+    o_masks = carve(head->mask_bytes);
+    o_pcm = carve(head->pcm_bytes);
+    head->head_bytes = off;
+  }
   const size_t o_tstats = carve(sizeof(float) * kStatsPerTile * tiles.size());
   const size_t o_mean = carve(sizeof(float) * kMel * n_utts);
   const size_t o_istd = carve(sizeof(float) * kMel * n_utts);
   const size_t o_mv = carve(sizeof(float) * n_utts);
-  const size_t o_g = carve(sizeof(float) * 2 * kMel);
   const size_t o_ustats = carve(sizeof(double) * kStatsPerTile * n_utts);
-  const size_t o_sched = carve(sizeof(int) * 2);
-  const size_t o_row0 = carve(sizeof(long long) * n_utts);
+  if (head == nullptr) {
+    o_g = carve(sizeof(float) * 2 * kMel);
+    o_sched = carve(sizeof(int) * 2);
+    o_row0 = carve(sizeof(long long) * n_utts);
+  }
   DeviceGuard guard(ctx->device);
   cudaError_t e = guard.err;
   if (e == cudaSuccess) e = pool_alloc(ctx, off, &p->d_ws, &p->ws_cap);
@@ -499,6 +552,24 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
       row0[u] = acc;
       acc += p->h_utts[u].n_frames;
     }
+  }
+  if (head != nullptr) {  // js2t_batch_fbank uploads the head itself, on the execute stream
+    head->o_utts = o_utts;
+    head->o_tiles = o_tiles;
+    head->o_row0 = o_row0;
+    head->o_sched = o_sched;
+    head->o_g = o_g;
+    head->o_masks = o_masks;
+    head->o_pcm = o_pcm;
+    head->tiles.swap(tiles);
+    head->row0.swap(row0);
+    p->d_pcm = reinterpret_cast<const uint8_t*>(base + o_pcm);
+    if (head->mask_bytes) {
+      p->d_masks = reinterpret_cast<int*>(base + o_masks);
+      p->masks_in_ws = true;
+    }
+    *out = p;
+    return JS2T_OK;
   }
   // Asynchronous upload on the context's own stream.  The sources are pageable: cudaMemcpyAsync returns
   // once they have been staged (so `tiles` may go out of scope), and the DMA itself is ordered on
@@ -548,7 +619,7 @@ static int plan_destroy_impl(js2t_plan* plan, bool wait) {
   if (wait) plan_quiesce(plan);
   else if (plan->ready_ev) cudaEventSynchronize(plan->ready_ev);
   if (plan->ready_ev) cudaEventDestroy(plan->ready_ev);
-  if (plan->d_masks) pool_free(plan->ctx, plan->d_masks, plan->masks_cap);
+  if (plan->d_masks && !plan->masks_in_ws) pool_free(plan->ctx, plan->d_masks, plan->masks_cap);
   if (plan->d_dbg) cudaFree(plan->d_dbg);
   if (plan->d_ws) pool_free(plan->ctx, plan->d_ws, plan->ws_cap);
   delete plan;
@@ -1178,6 +1249,244 @@ int js2t_pack_pcm(int n_utts, const void* const* src, const int64_t* n_bytes, co
     return JS2T_OK;
   }
   pool->run(chunks, helpers);
+  return JS2T_OK;
+}
+
+// One call per batch for callers that hold the utterances in host memory (the per-batch route of the
+// reference's data path: collate_fn -> Batch, joeynmt/datasets.py:221-225, batch.py:114-121).
+int js2t_batch_fbank(js2t_ctx* ctx, int n_utts, const void* const* pcm_host, const int64_t* n_samples,
+                     const uint8_t* is_f32, const js2t_batch_opts* o, float* out_dev, int64_t out_capacity_rows,
+                     void* stream_, js2t_plan** plan_out) {
+  if (ctx == nullptr || pcm_host == nullptr || n_samples == nullptr || o == nullptr || out_dev == nullptr)
+    return fail(JS2T_ERR_INVALID, "js2t_batch_fbank: NULL argument");
+  if (n_utts <= 0) return fail(JS2T_ERR_INVALID, "js2t_batch_fbank: n_utts = %d", n_utts);
+  if (!ctx->tables_set) return fail(JS2T_ERR_STATE, "js2t_ctx_set_tables has not been called");
+  if (o->cmvn_mode != JS2T_CMVN_NONE && o->cmvn_mode != JS2T_CMVN_UTTERANCE && o->cmvn_mode != JS2T_CMVN_GLOBAL)
+    return fail(JS2T_ERR_INVALID, "js2t_batch_fbank: CMVN mode %d", o->cmvn_mode);
+  if (o->cmvn_mode == JS2T_CMVN_GLOBAL && (o->global_mean80 == nullptr || o->global_istd80 == nullptr))
+    return fail(JS2T_ERR_STATE, "global CMVN requested but no statistics were given");
+  const int n_masks = o->mask_table != nullptr ? o->n_fmask + o->n_tmask : 0;
+  if (o->n_fmask < 0 || o->n_tmask < 0) return fail(JS2T_ERR_INVALID, "negative mask count");
+  if (n_masks > 0 && o->mask_value_mode != JS2T_MASK_VALUE_MEAN && o->mask_value_mode != JS2T_MASK_VALUE_CONST)
+    return fail(JS2T_ERR_INVALID, "unknown mask value mode %d", o->mask_value_mode);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DeviceGuard guard(ctx->device);
+  JS2T_CUDA(guard.err);
+  static const bool trace = getenv("JS2T_BATCH_TRACE") != nullptr;  // tuning aid: host time per phase to stderr
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto t_start = now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    const auto t1 = now();
+    fprintf(stderr, "  js2t_batch_fbank %-10s %7.1f us\n", what,
+            std::chrono::duration<double, std::micro>(t1 - t_start).count());
+    t_start = t1;
+  };
+
+  // ---- geometry: utterances back to back, 16-byte aligned ---------------------------------------------
+  std::vector<int64_t> off((size_t)n_utts), bytes((size_t)n_utts);
+  int64_t pcm_bytes = 0;
+  for (int u = 0; u < n_utts; ++u) {
+    if (n_samples[u] < 0) return fail(JS2T_ERR_INVALID, "utterance %d: negative length", u);
+    if (pcm_host[u] == nullptr && n_samples[u] > 0) return fail(JS2T_ERR_INVALID, "js2t_batch_fbank: pcm_host[%d] is NULL", u);
+    off[(size_t)u] = pcm_bytes;
+    bytes[(size_t)u] = n_samples[u] * ((is_f32 != nullptr && is_f32[u]) ? 4 : 2);
+    pcm_bytes += (bytes[(size_t)u] + 15) / 16 * 16;
+  }
+  BatchHead head;
+  head.pcm_bytes = (size_t)std::max<int64_t>(pcm_bytes, 16);
+  head.mask_bytes = sizeof(int32_t) * 2 * (size_t)n_masks * (size_t)n_utts;
+  js2t_plan* plan = nullptr;
+  const int rc = plan_create_common(ctx, n_utts, off.data(), n_samples, is_f32, o->max_frames, nullptr, o->layout,
+                                    o->pad_tmax, o->pad_value, &plan, &head);
+  if (rc != JS2T_OK) return rc;
+  if (plan->out_rows > out_capacity_rows) {
+    const long long need = plan->out_rows;
+    plan_destroy_impl(plan, false);
+    return fail(JS2T_ERR_INVALID, "js2t_batch_fbank: out_dev holds %lld rows, the batch needs %lld",
+                (long long)out_capacity_rows, need);
+  }
+
+  lap("plan");
+  // ---- reap what earlier calls left behind, take a staging slot -----------------------------------------
+  js2t_ctx::StagingSlot* slot = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(ctx->batch_mu);
+    while (!ctx->retired.empty() &&
+           (ctx->retired.size() > 8 || cudaEventQuery(ctx->retired.front().first) == cudaSuccess)) {
+      cudaEventSynchronize(ctx->retired.front().first);
+      ctx->spare_events.push_back(ctx->retired.front().first);
+      plan_destroy_impl(ctx->retired.front().second, false);
+      ctx->retired.erase(ctx->retired.begin());
+    }
+    cudaGetLastError();  // cudaEventQuery's cudaErrorNotReady is not an error
+    lap("reap");
+    for (auto& sl : ctx->slots)
+      if (sl.in_flight && cudaEventQuery(sl.ev) == cudaSuccess) sl.in_flight = false;
+    cudaGetLastError();
+    for (auto& sl : ctx->slots)
+      if (!sl.in_flight && sl.cap >= head.head_bytes && (slot == nullptr || sl.cap < slot->cap)) slot = &sl;
+    if (slot == nullptr) {
+      for (auto& sl : ctx->slots)
+        if (!sl.in_flight) slot = &sl;  // a free slot that is too small: re-allocated below
+      if (slot == nullptr && ctx->slots.size() < 4) {
+        ctx->slots.reserve(4);  // pointers into the vector stay valid
+        ctx->slots.emplace_back();
+        slot = &ctx->slots.back();
+      }
+      if (slot == nullptr) {  // all four in flight: wait for the first one
+        slot = &ctx->slots.front();
+        cudaEventSynchronize(slot->ev);
+        slot->in_flight = false;
+        lap("slot-wait");
+      }
+    }
+    slot->in_flight = true;
+  }
+  cudaError_t e = cudaSuccess;
+  if (slot->cap < head.head_bytes) {
+    if (slot->host) cudaFreeHost(slot->host);
+    slot->host = nullptr;
+    slot->cap = 0;
+    const size_t cap = align_up(head.head_bytes + head.head_bytes / 4, 1 << 20);
+    e = cudaHostAlloc(reinterpret_cast<void**>(&slot->host), cap, cudaHostAllocDefault);
+    if (e == cudaSuccess) slot->cap = cap;
+  }
+  if (e == cudaSuccess && slot->ev == nullptr) e = cudaEventCreateWithFlags(&slot->ev, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    slot->in_flight = false;
+    plan_destroy_impl(plan, false);
+    return fail(JS2T_ERR_CUDA, "js2t_batch_fbank: staging slot: %s", cudaGetErrorString(e));
+  }
+
+  lap("slot");
+  // ---- fill the slot: descriptors, zeroed scheduler counters, statistics, masks, PCM ----------------------
+  char* h = slot->host;
+  memcpy(h + head.o_utts, plan->h_utts.data(), sizeof(UttDesc) * (size_t)n_utts);
+  memcpy(h + head.o_tiles, head.tiles.data(), sizeof(TileDesc) * head.tiles.size());
+  memcpy(h + head.o_row0, head.row0.data(), sizeof(long long) * (size_t)n_utts);
+  memset(h + head.o_sched, 0, sizeof(int) * 2);
+  if (o->cmvn_mode == JS2T_CMVN_GLOBAL) {
+    float* g = reinterpret_cast<float*>(h + head.o_g);
+    for (int b = 0; b < kMel; ++b) {
+      g[b] = (float)o->global_mean80[b];
+      g[kMel + b] = (float)o->global_istd80[b];
+    }
+    plan->global_stats_set = true;
+  }
+  if (n_masks > 0) memcpy(h + head.o_masks, o->mask_table, head.mask_bytes);
+  const int prc = js2t_pack_pcm(n_utts, pcm_host, bytes.data(), off.data(), h + head.o_pcm, (int64_t)head.pcm_bytes, 0);
+  if (prc != JS2T_OK) {
+    slot->in_flight = false;
+    plan_destroy_impl(plan, false);
+    return prc;
+  }
+
+  lap("pack");
+  // ---- one transfer, then the kernels ---------------------------------------------------------------------
+  // The transfer runs on the context's own copy stream and the kernels wait for its event: the upload of this
+  // batch overlaps the kernels of the previous one (same caller stream), the device is then bound by the larger
+  // of the two instead of their sum.  The workspace it writes is not in use: a plan's buffer returns to the pool
+  // only after the event behind its last kernel has completed.
+  e = cudaMemcpyAsync(plan->d_ws, h, head.head_bytes, cudaMemcpyHostToDevice, ctx->upload_stream);
+  if (e == cudaSuccess) e = cudaEventRecord(slot->ev, ctx->upload_stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, slot->ev, 0);
+  if (e != cudaSuccess) {
+    cudaStreamSynchronize(stream);
+    slot->in_flight = false;
+    plan_destroy_impl(plan, false);
+    return fail(JS2T_ERR_CUDA, "js2t_batch_fbank: upload: %s", cudaGetErrorString(e));
+  }
+  lap("memcpy");
+  plan->streams.push_back(stream);  // stream order puts the kernels behind the upload: no ready event
+  plan->cmvn_mode = o->cmvn_mode;
+  plan->norm_means = o->norm_means != 0;
+  plan->norm_vars = o->norm_vars != 0;
+  plan->before = o->before != 0;
+  if (n_masks > 0) {
+    plan->n_fmask = o->n_fmask;
+    plan->n_tmask = o->n_tmask;
+    plan->mask_value_mode = o->mask_value_mode;
+    plan->mask_value_const = o->mask_value_const;
+    plan->has_masks = true;
+  }
+  const int xrc = run_pipeline(plan, plan->d_pcm, out_dev, stream, /*from_pcm=*/true);
+  lap("launch");
+  if (xrc != JS2T_OK || plan_out != nullptr) {
+    if (xrc != JS2T_OK) {
+      cudaStreamSynchronize(stream);
+      plan_destroy_impl(plan, false);
+      return xrc;
+    }
+    *plan_out = plan;  // the caller destroys it (js2t_plan_destroy, or _completed behind its own event)
+    return JS2T_OK;
+  }
+  // the context keeps the plan until the event behind its last kernel has completed
+  {
+    std::lock_guard<std::mutex> lk(ctx->batch_mu);
+    cudaEvent_t ev = nullptr;
+    if (!ctx->spare_events.empty()) {
+      ev = ctx->spare_events.back();
+      ctx->spare_events.pop_back();
+    } else if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+      ev = nullptr;
+    }
+    if (ev == nullptr || cudaEventRecord(ev, stream) != cudaSuccess) {
+      cudaStreamSynchronize(stream);
+      if (ev) cudaEventDestroy(ev);
+      plan_destroy_impl(plan, false);
+    } else {
+      ctx->retired.emplace_back(ev, plan);
+    }
+  }
+  return JS2T_OK;
+}
+
+// SpecAugment mask tables of a whole batch, drawn from the caller's 32-bit generator — an exact replay of the
+// reference's per-item draws (joeynmt/data_augmentation.py:48-70: np.random.randint(0, hi) four times per mask
+// pair), which numpy's legacy RandomState serves with masked rejection on 32-bit outputs: hi - 1 == 0 consumes
+// nothing, otherwise outputs are drawn until (output & mask) <= hi - 1, mask = the smallest 2^k - 1 >= hi - 1.
+// next_uint32 / rng_state are numpy's own (BitGenerator.ctypes), so the stream advances exactly as if the
+// reference's loop had run.  Pure host code.
+int js2t_specaug_replay(js2t_next_uint32_fn next_uint32, void* rng_state, int n_utts, const int32_t* n_frames,
+                        int num_freqs, int freq_mask_n, int freq_mask_f, int time_mask_n, int time_mask_t,
+                        double time_mask_p, int32_t* table_out) {
+  if (next_uint32 == nullptr || n_frames == nullptr || table_out == nullptr)
+    return fail(JS2T_ERR_INVALID, "js2t_specaug_replay: NULL argument");
+  if (n_utts < 0 || freq_mask_n < 0 || time_mask_n < 0 || freq_mask_f < 1 || num_freqs < freq_mask_f)
+    return fail(JS2T_ERR_INVALID, "js2t_specaug_replay: mask configuration outside the replayed range");
+  auto bounded = [&](long long hi) -> long long {  // np.random.randint(0, hi), hi >= 1
+    const unsigned long long rng = (unsigned long long)(hi - 1);
+    if (rng == 0) return 0;
+    unsigned long long mask = rng;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    for (;;) {
+      const unsigned long long v = next_uint32(rng_state) & mask;
+      if (v <= rng) return (long long)v;
+    }
+  };
+  const int n_masks = freq_mask_n + time_mask_n;
+  for (int u = 0; u < n_utts; ++u) {
+    int32_t* row = table_out + (size_t)u * n_masks * 2;
+    for (int i = 0; i < 2 * n_masks; ++i) row[i] = 0;
+    const long long T = n_frames[u];
+    if (T <= 0) continue;                    // :48-52 the spectrogram is returned untouched
+    for (int m = 0; m < freq_mask_n; ++m) {  // :54-58 (num_freqs - f >= 1 because f < freq_mask_f <= num_freqs)
+      const long long f = bounded(freq_mask_f);
+      const long long f0 = bounded(num_freqs - f);
+      row[2 * m] = (int32_t)f0;
+      row[2 * m + 1] = (int32_t)f;
+    }
+    long long max_t = (long long)floor((double)T * time_mask_p);  // :60-62
+    if (time_mask_t < max_t) max_t = time_mask_t;
+    if (max_t < 1) continue;                                       // :63-64 frequency masks only
+    for (int m = 0; m < time_mask_n; ++m) {                        // :66-70 (T - t >= 1 because t < max_t <= T)
+      const long long tt = bounded(max_t);
+      const long long t0 = bounded(T - tt);
+      row[2 * (freq_mask_n + m)] = (int32_t)t0;
+      row[2 * (freq_mask_n + m) + 1] = (int32_t)tt;
+    }
+  }
   return JS2T_OK;
 }
 

@@ -120,6 +120,10 @@ def _as_1d_pcm(w: Array) -> np.ndarray:
     return np.ascontiguousarray(w, dtype=np.float32)
 
 
+_I16, _F32 = np.dtype(np.int16), np.dtype(np.float32)
+_addressof, _c_char = ctypes.addressof, ctypes.c_char
+
+
 class PackedPCM:
     """Ragged batch packed into one pinned byte buffer, every utterance 16-byte aligned."""
 
@@ -420,6 +424,10 @@ def fbank_cmvn_specaug_ragged(
     :returns: (features on the GPU — ragged ``(sum T, 80)`` or padded ``(B, Tmax, 80)`` —, n_frames)
     """
     _require_cuda()
+    if dither_noise is None:
+        return _batch_fbank(waveforms, cmvn, masks, n_fmask, n_tmask, mask_value, max_frames, layout,
+                            pad_value, global_stats)
+    # dither compatibility / test mode: the step-by-step route (plan, separate uploads)
     st = _staging_state()
     st.reap()
     slot = []
@@ -442,11 +450,9 @@ def fbank_cmvn_specaug_ragged(
                       cmvn.get("before", True))
     if masks is not None:
         plan.set_masks(masks, n_fmask, n_tmask, mask_value)
-    noise_dev = None
-    if dither_noise is not None:
-        noise_dev = torch.as_tensor(dither_noise, dtype=torch.float32).contiguous().to(
-            f"cuda:{plan.ctx.device}")
-        plan.set_dither(noise_dev)
+    noise_dev = torch.as_tensor(dither_noise, dtype=torch.float32).contiguous().to(
+        f"cuda:{plan.ctx.device}")
+    plan.set_dither(noise_dev)
     stream = torch.cuda.current_stream(plan.ctx.device)
     dev_pcm = packed.host[:max(packed.nbytes, 16)].to(f"cuda:{plan.ctx.device}", non_blocking=True)
     st.release_after(slot[0], stream)   # the staging slot is free again once the H2D copy has read it
@@ -455,6 +461,70 @@ def fbank_cmvn_specaug_ragged(
     # asynchronous return: the plan's workspace and the device PCM outlive the enqueued kernels (retired
     # behind an event on this stream); `out` is ordered on the current stream like any torch result
     st.retire(plan, (dev_pcm, noise_dev), stream)
+    return out, n_frames
+
+
+def _batch_fbank(waveforms, cmvn, masks, n_fmask, n_tmask, mask_value, max_frames, layout, pad_value,
+                 global_stats, device: Optional[int] = None) -> Tuple[torch.Tensor, np.ndarray]:
+    """The whole batch through ONE C call (``js2t_batch_fbank``): gather into a pinned staging slot of the
+    context, one H2D transfer for PCM + descriptors + masks + statistics, three kernel launches; returns as
+    soon as the work is enqueued on torch's current stream (``out`` is ordered on it like any torch result)."""
+    ctx = get_context(device)
+    lib = _lib.load()
+    i16 = _I16
+    # (fast path for what the callers hand over: contiguous 1-D int16 / float32 numpy arrays)
+    arrs = [w if (type(w) is np.ndarray and w.ndim == 1 and (w.dtype == i16 or w.dtype == _F32)
+                  and w.flags.c_contiguous) else _as_1d_pcm(w) for w in waveforms]
+    n = len(arrs)
+    n_samples = np.array([a.shape[0] for a in arrs], np.int64)
+    is_f32 = np.array([a.dtype != i16 for a in arrs], np.uint8)
+    # (a too-short utterance gives 0 frames here; the C call rejects it with JS2T_ERR_SHORT_INPUT before
+    # anything is enqueued)
+    n_frames = np.where(n_samples >= 400, 1 + (n_samples - 400) // 160, 0).astype(np.int32)
+    mf = None
+    if max_frames is not None:
+        mf = np.ascontiguousarray(max_frames, np.int32)
+        n_frames = np.where(mf > 0, np.minimum(n_frames, mf), n_frames).astype(np.int32)
+    padded = layout == "padded"
+    tmax = int(n_frames.max()) if n else 0
+    rows = n * tmax if padded else int(n_frames.sum())
+    dev = f"cuda:{ctx.device}"
+    out = torch.empty((n, tmax, NUM_MEL) if padded else (rows, NUM_MEL), dtype=torch.float32, device=dev)
+    o = _lib.BatchOpts()
+    o.layout = {"ragged": _lib.LAYOUT_RAGGED, "padded": _lib.LAYOUT_PADDED}[layout]
+    o.pad_tmax = 0
+    o.pad_value = float(pad_value)
+    keep = [arrs, n_samples, is_f32, mf]
+    if global_stats is not None:
+        kw = dict(cmvn or {})
+        gm = np.ascontiguousarray(global_stats[0], np.float64)
+        gi = np.ascontiguousarray(global_stats[1], np.float64)
+        assert gm.shape == (NUM_MEL,) and gi.shape == (NUM_MEL,)
+        keep += [gm, gi]
+        o.cmvn_mode = _lib.CMVN_GLOBAL
+        o.global_mean80, o.global_istd80 = gm.ctypes.data, gi.ctypes.data
+    else:
+        kw = cmvn or {}
+        o.cmvn_mode = _lib.CMVN_NONE if cmvn is None else _lib.CMVN_UTTERANCE
+    o.norm_means, o.norm_vars = int(kw.get("norm_means", True)), int(kw.get("norm_vars", True))
+    o.before = int(kw.get("before", True))
+    if masks is not None and n_fmask + n_tmask > 0:
+        tb = np.ascontiguousarray(masks, np.int32)
+        assert tb.shape == (n, n_fmask + n_tmask, 2), tb.shape
+        keep.append(tb)
+        o.n_fmask, o.n_tmask, o.mask_table = int(n_fmask), int(n_tmask), tb.ctypes.data
+        o.mask_value_mode = _lib.MASK_VALUE_MEAN if mask_value is None else _lib.MASK_VALUE_CONST
+        o.mask_value_const = 0.0 if mask_value is None else float(mask_value)
+    if mf is not None:
+        o.max_frames = mf.ctypes.data
+    try:  # (the cheapest way to an ndarray's address; read-only arrays take the slower attribute)
+        ptrs = np.array([_addressof(_c_char.from_buffer(a)) for a in arrs], np.uint64)
+    except (TypeError, ValueError):
+        ptrs = np.array([a.ctypes.data for a in arrs], np.uint64)
+    _lib.check(lib.js2t_batch_fbank(ctx.handle, n, ptrs.ctypes.data, n_samples.ctypes.data, is_f32.ctypes.data,
+                                    ctypes.byref(o), out.data_ptr(), rows, _stream_ptr(device=ctx.device),
+                                    None))
+    del keep  # everything the call read from the host has been copied when it returns
     return out, n_frames
 
 

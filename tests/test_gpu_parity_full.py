@@ -301,3 +301,108 @@ def test_dither_compat_mode_vs_torchaudio(fe, fixtures_pcm):
     # zero noise == dither off, bit for bit
     zero, _ = fe.fbank_cmvn_specaug_ragged(waves, dither_noise=np.zeros_like(noise))
     assert np.array_equal(zero.cpu().numpy(), plain)
+
+
+# ---- js2t_batch_fbank: the one-call per-batch entry point ------------------------------------------------
+def _mixed_batch(rng, lens):
+    waves = []
+    for i, n in enumerate(lens):
+        w = (np.cumsum(rng.randint(-400, 401, n)) % 20001 - 10000).astype(np.int16)
+        waves.append(w.astype(np.float32) / np.float32(32768.0) if i % 3 == 1 else w)
+    return waves
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", ["ragged", "padded"])
+@pytest.mark.parametrize("mode", ["raw", "utterance", "utterance_after_masks", "global_masks"])
+def test_batch_call_matches_the_step_by_step_route(layout, mode):
+    """``js2t_batch_fbank`` (host waveforms in, one transfer, kernels enqueued: what
+    ``frontend.fbank_cmvn_specaug_ragged`` and through it ``SpeechProcessor.process_batch`` /
+    ``SpeechBatchCollator`` call) must give bit for bit what the explicit route gives — ``js2t_pack_pcm`` ->
+    ``js2t_plan_create`` -> ``js2t_plan_set_*`` -> ``js2t_fbank_execute`` — which the tests above pin to the
+    oracle (tokenizers.py:458-494 order: truncation -> CMVN -> SpecAugment, pad_features :130-170)."""
+    import torch
+    from joeys2t_b200 import frontend
+
+    rng = np.random.RandomState(11)
+    lens = [400, 559, 400 + 160 * 31, 400 + 160 * 32, 5521, 16000 * 2 + 17, 16000 * 5, 16000 * 9 + 3]
+    waves = _mixed_batch(rng, lens)
+    max_frames = [0, 0, 20, 0, 0, 150, 0, 0]
+    T = np.array([1 + (n - 400) // 160 for n in lens])
+    T = np.where(np.array(max_frames) > 0, np.minimum(T, max_frames), T)
+    n_f, n_t = 2, 2
+    table = np.zeros((len(waves), n_f + n_t, 2), np.int32)
+    for u in range(len(waves)):
+        table[u, :n_f, 0] = rng.randint(0, 70, n_f)
+        table[u, :n_f, 1] = rng.randint(0, 12, n_f)
+        table[u, n_f:, 0] = rng.randint(0, max(int(T[u]), 1), n_t)
+        table[u, n_f:, 1] = rng.randint(0, 30, n_t)
+    gstats = (rng.uniform(-8, 2, 80), rng.uniform(0.2, 1.5, 80))
+    kw = dict(max_frames=max_frames, layout=layout, pad_value=1.0)
+    if mode == "utterance":
+        kw.update(cmvn=dict(norm_means=True, norm_vars=True, before=True))
+    elif mode == "utterance_after_masks":
+        kw.update(cmvn=dict(norm_means=True, norm_vars=False, before=False), masks=table, n_fmask=n_f, n_tmask=n_t)
+    elif mode == "global_masks":
+        kw.update(cmvn=dict(norm_means=True, norm_vars=True, before=True), global_stats=gstats, masks=table,
+                  n_fmask=n_f, n_tmask=n_t, mask_value=0.0)
+    got, n_frames = frontend.fbank_cmvn_specaug_ragged(waves, **kw)
+    assert n_frames.tolist() == T.tolist()
+
+    packed = frontend.PackedPCM(waves)
+    plan = frontend.Plan(packed.n_samples, packed.byte_off, packed.is_f32, max_frames=max_frames, layout=layout,
+                         pad_value=1.0)
+    if mode == "global_masks":
+        plan.set_cmvn("global", True, True, True)
+        plan.set_global_stats(*gstats)
+    elif mode != "raw":
+        plan.set_cmvn("utterance", **kw["cmvn"])
+    if "masks" in kw:
+        plan.set_masks(table, n_f, n_t, kw.get("mask_value"))
+    ref = plan.execute(packed.to_device())
+    torch.cuda.synchronize()
+    a, b = ref.cpu().numpy().reshape(-1, 80), got.cpu().numpy().reshape(-1, 80)
+    assert a.shape == b.shape and np.isfinite(a).all()
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    plan.close()
+    # many calls back to back: staging slots and retired plans are recycled behind their events
+    outs = [frontend.fbank_cmvn_specaug_ragged(waves, **kw)[0] for _ in range(12)]
+    torch.cuda.synchronize()
+    for o in outs:
+        assert np.array_equal(o.cpu().numpy().reshape(-1, 80).view(np.uint32), a.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_batch_call_errors_enqueue_nothing():
+    """A too-short utterance (helpers_for_audio.py:41-68 -> kaldi.py's window-size assertion) or an output
+    buffer that is too small is reported by ``js2t_batch_fbank`` before anything is enqueued."""
+    import ctypes
+
+    import torch
+    from joeys2t_b200 import _lib, frontend
+
+    waves = [np.zeros(16000, np.int16), np.zeros(399, np.int16)]
+    with pytest.raises(_lib.Js2tError) as ei:
+        frontend.fbank_cmvn_specaug_ragged(waves)
+    assert ei.value.code == _lib.ERR_SHORT_INPUT and "choose a window size 400" in str(ei.value)
+    ctx = frontend.get_context()
+    lib = _lib.load()
+    w = np.zeros(16000, np.int16)
+    out = torch.empty((10, 80), dtype=torch.float32, device="cuda")  # 98 rows needed
+    o = _lib.BatchOpts()
+    o.layout, o.pad_value, o.cmvn_mode = _lib.LAYOUT_RAGGED, 1.0, _lib.CMVN_NONE
+    ptrs = np.array([w.ctypes.data], np.uint64)
+    ns = np.array([16000], np.int64)
+    rc = lib.js2t_batch_fbank(ctx.handle, 1, ptrs.ctypes.data, ns.ctypes.data, None, ctypes.byref(o),
+                              out.data_ptr(), 10, 0, None)
+    assert rc == _lib.ERR_INVALID and b"98" in lib.js2t_last_error()
+    # a caller-owned plan: statistics can be read back, the caller destroys it
+    out = torch.empty((98, 80), dtype=torch.float32, device="cuda")
+    o.cmvn_mode, o.norm_means, o.norm_vars, o.before = _lib.CMVN_UTTERANCE, 1, 1, 1
+    h = ctypes.c_void_p()
+    rc = lib.js2t_batch_fbank(ctx.handle, 1, ptrs.ctypes.data, ns.ctypes.data, None, ctypes.byref(o),
+                              out.data_ptr(), 98, torch.cuda.current_stream().cuda_stream, ctypes.byref(h))
+    assert rc == _lib.OK and h.value
+    torch.cuda.synchronize()
+    assert int(lib.js2t_plan_total_frames(h)) == 98
+    assert lib.js2t_plan_destroy(h) == _lib.OK
