@@ -302,6 +302,15 @@ __host__ __device__ constexpr int mel_bin_hi(int m0, int m1) {
   return r;
 }
 
+// JS2T_LOG_AT_STORE (default): the mel runs leave the filter SUMS in the out tile and the store phase takes
+// the log — the same operation on the same value (results are bit-identical), but ~4 instructions per filter
+// move out of the eight per-warp code streams (80 copies) into code that all warps share (12 per thread).  The
+// loop body does not fit the instruction caches and the SM-wide footprint is what the fetch stalls follow:
+// 4 584 -> 4 328 SASS instructions, 177.8 -> 173.0 us per launch (profiles/r2_icache_ab.txt).
+#ifndef JS2T_LOG_AT_STORE
+#define JS2T_LOG_AT_STORE 1
+#endif
+
 // All of the run's power-spectrum values are loaded into registers first (one batch of independent
 // LDS), then the two slopes of every triangle are accumulated from registers: the shared-memory
 // latency is paid once per run instead of once per bin (the stores of the results would otherwise
@@ -320,7 +329,7 @@ __device__ __forceinline__ void mel_group(const float* __restrict__ Pl, float* _
       if constexpr ((s) < M1) hi_acc = fmaf(c_mel_wu[k], p, hi_acc);                 \
       if constexpr ((s) > M0) lo_acc = fmaf(c_mel_wd[k], p, lo_acc);                 \
     }                                                                                \
-    if constexpr ((s) > M0) orow[(s)-1] = log_floor(lo_acc);                         \
+    if constexpr ((s) > M0) orow[(s)-1] = JS2T_LOG_AT_STORE ? lo_acc : log_floor(lo_acc); \
     lo_acc = hi_acc;                                                                 \
     hi_acc = 0.f;                                                                    \
   }
@@ -985,6 +994,10 @@ __global__ void JS2T_FBANK_BOUNDS fbank_tile_kernel(const FbankLaunch p) {
               x[3 * i + 1] = src[i * kOutStride + 32];
               x[3 * i + 2] = src[i * kOutStride + 64];  // lanes >= 16: row padding, zeroed below
             }
+            if (JS2T_LOG_AT_STORE) {
+#pragma unroll
+              for (int i = 0; i < 12; ++i) x[i] = log_floor(x[i]);
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               st_keep(dst + i * kMel, x[3 * i], keep);
@@ -1008,9 +1021,10 @@ __global__ void JS2T_FBANK_BOUNDS fbank_tile_kernel(const FbankLaunch p) {
                 const bool valid = f < nf;
                 const float* src = sOut + f * kOutStride + lane;
                 float* dst = out_tile + f * kMel + lane;
-                const float x0 = valid ? src[0] : p.pad_value;
-                const float x1 = valid ? src[32] : p.pad_value;
-                const float x2 = (valid && c2ok) ? src[64] : p.pad_value;
+                const float x0 = valid ? (JS2T_LOG_AT_STORE ? log_floor(src[0]) : src[0]) : p.pad_value;
+                const float x1 = valid ? (JS2T_LOG_AT_STORE ? log_floor(src[32]) : src[32]) : p.pad_value;
+                const float x2 =
+                    (valid && c2ok) ? (JS2T_LOG_AT_STORE ? log_floor(src[64]) : src[64]) : p.pad_value;
                 st_keep(dst, x0, keep);
                 st_keep(dst + 32, x1, keep);
                 if (c2ok) st_keep(dst + 64, x2, keep);
@@ -1048,6 +1062,10 @@ __global__ void JS2T_FBANK_BOUNDS fbank_tile_kernel(const FbankLaunch p) {
             x[3 * i] = src[0];
             x[3 * i + 1] = src[32];
             x[3 * i + 2] = src[64];  // lanes >= 16: inside the padded row, never stored
+          }
+          if (JS2T_LOG_AT_STORE) {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) x[i] = log_floor(x[i]);
           }
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
