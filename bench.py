@@ -436,7 +436,14 @@ def run_b200(args):
     # stream.  The three kernels of a step are chained by programmatic dependent launch; an event
     # recorded between two kernels would serialise them again, so the per-kernel events of the roofline
     # line are taken in a second, identical region (B) right after, whose own step time is reported too.
+    # The device spins for a moment in front of the region (a one-thread clock loop, torch.cuda._sleep) while
+    # the host enqueues the steps behind it: a 20-step region is 4 ms of device time, and on a box where N
+    # ranks, their NCCL / sampling threads and the driver share the host cores, one descheduled launching
+    # thread otherwise shows up as a step time twice the real one (seen once at N = 8: 0.43 ms against 0.21 ms
+    # in the 60-ms region of the same run).  The events still bracket exactly `steps` steps on the device.
+    head_start_ms = min(6.0, 0.04 * args.steps)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(int(head_start_ms * 1e-3 * 1.9e9))  # pylint: disable=protected-access
     ev0.record()
     for i in range(args.steps):
         step(i)
@@ -539,6 +546,7 @@ def run_b200(args):
                 "frames_per_step_per_gpu": frames_launch,
                 "audio_hours_per_step_per_gpu": float(np.mean(hours_per_step)),
                 "pcm": "resident in HBM", "cmvn": wl["cmvn"] + " (norm_means, norm_vars, before)",
+                "enqueue_head_start_ms": head_start_ms,
                 "cmvn_path": "fbank epilogue" if wl["cmvn"] == "global" else "fbank+stats, finalize, apply kernels",
                 "l2": f"every step uses its own input and output buffers out of a ring of {n_buf} "
                       f"({working_set / 1e9:.2f} GB of inputs+outputs per GPU, >> the 126 MB L2; {R} distinct "
