@@ -663,10 +663,12 @@ __global__ void JS2T_FBANK_BOUNDS fbank_tile_kernel(const FbankLaunch p) {
     const bool next_tma = has_next && nxt.nf > 0;
     const bool next_early = next_tma && cur_slots + (unsigned)tile_slots(nxt) <= 2u;
     if (is_sched && next_early) prefetch_tile(p, nxt, sRaw, sBar, kslot + cur_slots);
-    if (kMode == kModeNormKnown && p.masks != nullptr) {
+    if (kMode == kModeNormKnown && p.masks != nullptr && cur.nf > 0) {
       // this utterance's mask table and fill value -> shared memory (read two barriers later)
       // (cp.async: fire and forget now, waited for just before the barrier in front of the epilogue,
-      // so the global-memory latency is hidden behind the FFT and costs no registers)
+      // so the global-memory latency is hidden behind the FFT and costs no registers; not for pure padding
+      // tiles, which neither need the table nor reach the wait: their copies would still be in flight when
+      // the next tile issues its own to the same words)
       const int n2 = 2 * (p.n_fmask + p.n_tmask);
       if (tid < n2)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&sMaskTab[tid])),
