@@ -8,6 +8,7 @@ The per-item wrappers with the reference's signatures (``helpers_for_audio.py``,
 ``data_augmentation.py``, ``speech_processor.py``) are batch-of-one calls into this module.
 """
 import ctypes
+import os
 import threading
 from typing import List, Optional, Sequence, Tuple, Union
 
@@ -21,9 +22,22 @@ Array = Union[np.ndarray, torch.Tensor]
 
 _contexts = {}
 _contexts_lock = threading.Lock()
+_owner_pid: Optional[int] = None  # the process that created the device contexts
+
+
+def _check_not_forked():
+    """The reference's data path may run inside ``DataLoader(num_workers > 0)`` workers, which are forked
+    (SURVEY 8b).  A CUDA context does not survive ``fork``: a child that inherited this module's contexts would
+    fail inside the driver, or hang.  Fail here instead, with what to do about it."""
+    if _owner_pid is not None and _owner_pid != os.getpid():
+        raise RuntimeError(
+            "joeys2t_b200 was initialised in process %d and is now called from its forked child %d: CUDA "
+            "contexts do not survive fork().  Use DataLoader(num_workers=0) — the GPU front-end is faster than a "
+            "pool of CPU workers — or multiprocessing_context='spawn'." % (_owner_pid, os.getpid()))
 
 
 def _require_cuda():
+    _check_not_forked()  # (before any CUDA query: in a forked child even those may fail)
     if not torch.cuda.is_available():
         raise RuntimeError(
             "joeys2t_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
@@ -74,12 +88,15 @@ class Context:
 
 
 def get_context(device: Optional[int] = None) -> Context:
+    global _owner_pid
+    _check_not_forked()
     _require_cuda()
     if device is None:
         device = torch.cuda.current_device()
     with _contexts_lock:  # per-thread staging implies threaded callers
         if device not in _contexts:
             _contexts[device] = Context(device)
+            _owner_pid = os.getpid()
         return _contexts[device]
 
 

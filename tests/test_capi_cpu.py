@@ -150,3 +150,21 @@ def test_pack_pcm_gathers_ragged_batches():
     small = np.zeros(8, np.uint8)
     rc = lib.js2t_pack_pcm(len(arrs), ptrs, sizes.ctypes.data, off.ctypes.data, small.ctypes.data, 8, 1)
     assert rc == _lib.ERR_INVALID
+
+
+def test_a_forked_child_is_told_what_to_do():
+    """The reference's DataLoader workers are forked; a CUDA context does not survive fork, so a
+    child that inherited the module's contexts must get a clear error instead of a driver failure."""
+    import os
+
+    from joeys2t_b200 import frontend
+
+    old = frontend._owner_pid
+    try:
+        frontend._owner_pid = os.getpid() + 1  # as if the contexts had been created by the parent
+        with pytest.raises(RuntimeError, match="do not survive fork"):
+            frontend.get_context()
+        frontend._owner_pid = os.getpid()
+        frontend._check_not_forked()  # same process: fine
+    finally:
+        frontend._owner_pid = old

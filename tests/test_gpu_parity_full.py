@@ -406,3 +406,33 @@ def test_batch_call_errors_enqueue_nothing():
     torch.cuda.synchronize()
     assert int(lib.js2t_plan_total_frames(h)) == 98
     assert lib.js2t_plan_destroy(h) == _lib.OK
+
+
+@pytest.mark.gpu
+def test_forked_worker_gets_a_clear_error(fe, fixtures_pcm):
+    """``DataLoader(num_workers > 0)`` forks its workers (the reference's loaders do: datasets.py make_iter); a CUDA
+    context does not survive ``fork``.  A forked child that calls the front-end must fail with an explanation —
+    not inside the driver — and the parent must be unaffected."""
+    import os
+
+    fe.fbank_cmvn_specaug_ragged([fixtures_pcm[0][0]])  # the parent owns a context now
+    r, w = os.pipe()
+    pid = os.fork()
+    if pid == 0:  # child: no CUDA call may be made here
+        os.close(r)
+        try:
+            fe.fbank_cmvn_specaug_ragged([fixtures_pcm[0][0]])
+            msg = b"no error"
+        except RuntimeError as e:
+            msg = str(e).encode()
+        except BaseException as e:  # pylint: disable=broad-except
+            msg = b"other: " + repr(e).encode()
+        os.write(w, msg[:4000])
+        os._exit(0)
+    os.close(w)
+    got = os.read(r, 4096).decode()
+    os.waitpid(pid, 0)
+    os.close(r)
+    assert "do not survive fork" in got and "num_workers=0" in got, got
+    out, _ = fe.fbank_cmvn_specaug_ragged([fixtures_pcm[0][0]])
+    assert np.isfinite(out.cpu().numpy()).all()
