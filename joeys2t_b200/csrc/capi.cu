@@ -84,7 +84,9 @@ struct js2t_ctx {
     char* host = nullptr;
     size_t cap = 0;
     cudaEvent_t ev = nullptr;
-    bool in_flight = false;
+    // free -> filling (a call owns it: gather + upload being issued) -> pending (event recorded behind the upload;
+    // free again once it has completed).  Only the owner touches a filling slot; only recorded events are waited on.
+    bool filling = false, pending = false;
   };
   std::mutex batch_mu;
   std::vector<StagingSlot> slots;
@@ -1321,28 +1323,56 @@ int js2t_batch_fbank(js2t_ctx* ctx, int n_utts, const void* const* pcm_host, con
     }
     cudaGetLastError();  // cudaEventQuery's cudaErrorNotReady is not an error
     lap("reap");
-    for (auto& sl : ctx->slots)
-      if (sl.in_flight && cudaEventQuery(sl.ev) == cudaSuccess) sl.in_flight = false;
-    cudaGetLastError();
-    for (auto& sl : ctx->slots)
-      if (!sl.in_flight && sl.cap >= head.head_bytes && (slot == nullptr || sl.cap < slot->cap)) slot = &sl;
-    if (slot == nullptr) {
+  }
+  constexpr size_t kMaxSlots = 8;                       // enough for a few threads with a couple of batches in flight
+  constexpr size_t kMaxPinnedBytes = (size_t)512 << 20;  // ... as long as the pinned memory stays bounded
+  for (;;) {
+    js2t_ctx::StagingSlot* wait_for = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(ctx->batch_mu);
+      if (ctx->slots.capacity() < kMaxSlots) ctx->slots.reserve(kMaxSlots);  // pointers into the vector stay valid
       for (auto& sl : ctx->slots)
-        if (!sl.in_flight) slot = &sl;  // a free slot that is too small: re-allocated below
-      if (slot == nullptr && ctx->slots.size() < 4) {
-        ctx->slots.reserve(4);  // pointers into the vector stay valid
+        if (sl.pending && cudaEventQuery(sl.ev) == cudaSuccess) sl.pending = false;
+      cudaGetLastError();  // cudaEventQuery's cudaErrorNotReady is not an error
+      for (auto& sl : ctx->slots)
+        if (!sl.filling && !sl.pending && sl.cap >= head.head_bytes && (slot == nullptr || sl.cap < slot->cap)) slot = &sl;
+      if (slot == nullptr) {
+        for (auto& sl : ctx->slots)
+          if (!sl.filling && !sl.pending) slot = &sl;  // a free slot that is too small: re-allocated below
+      }
+      size_t pinned = 0;
+      for (auto& sl : ctx->slots) pinned += sl.cap;
+      if (slot == nullptr && ctx->slots.size() < kMaxSlots &&
+          (ctx->slots.size() < 2 || pinned + head.head_bytes <= kMaxPinnedBytes)) {
         ctx->slots.emplace_back();
         slot = &ctx->slots.back();
       }
-      if (slot == nullptr) {  // all four in flight: wait for the first one
-        slot = &ctx->slots.front();
-        cudaEventSynchronize(slot->ev);
-        slot->in_flight = false;
-        lap("slot-wait");
+      if (slot == nullptr) {  // every slot is busy: wait for an upload that has been issued (outside the lock)
+        for (auto& sl : ctx->slots)
+          if (sl.pending && !sl.filling) {
+            wait_for = &sl;
+            break;
+          }
+        if (wait_for != nullptr) wait_for->filling = true;  // ours from here on
+      } else {
+        slot->filling = true;
       }
     }
-    slot->in_flight = true;
+    if (slot != nullptr) break;
+    if (wait_for != nullptr) {
+      cudaEventSynchronize(wait_for->ev);
+      wait_for->pending = false;  // (filling: no other call looks at it)
+      slot = wait_for;
+      lap("slot-wait");
+      break;
+    }
+    std::this_thread::yield();  // all slots are being filled by other threads
   }
+  auto release_slot = [&](bool recorded) {
+    std::lock_guard<std::mutex> lk(ctx->batch_mu);
+    slot->pending = recorded;
+    slot->filling = false;
+  };
   cudaError_t e = cudaSuccess;
   if (slot->cap < head.head_bytes) {
     if (slot->host) cudaFreeHost(slot->host);
@@ -1354,7 +1384,7 @@ int js2t_batch_fbank(js2t_ctx* ctx, int n_utts, const void* const* pcm_host, con
   }
   if (e == cudaSuccess && slot->ev == nullptr) e = cudaEventCreateWithFlags(&slot->ev, cudaEventDisableTiming);
   if (e != cudaSuccess) {
-    slot->in_flight = false;
+    release_slot(false);
     plan_destroy_impl(plan, false);
     return fail(JS2T_ERR_CUDA, "js2t_batch_fbank: staging slot: %s", cudaGetErrorString(e));
   }
@@ -1377,7 +1407,7 @@ int js2t_batch_fbank(js2t_ctx* ctx, int n_utts, const void* const* pcm_host, con
   if (n_masks > 0) memcpy(h + head.o_masks, o->mask_table, head.mask_bytes);
   const int prc = js2t_pack_pcm(n_utts, pcm_host, bytes.data(), off.data(), h + head.o_pcm, (int64_t)head.pcm_bytes, 0);
   if (prc != JS2T_OK) {
-    slot->in_flight = false;
+    release_slot(false);
     plan_destroy_impl(plan, false);
     return prc;
   }
@@ -1392,11 +1422,13 @@ int js2t_batch_fbank(js2t_ctx* ctx, int n_utts, const void* const* pcm_host, con
   if (e == cudaSuccess) e = cudaEventRecord(slot->ev, ctx->upload_stream);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, slot->ev, 0);
   if (e != cudaSuccess) {
+    cudaStreamSynchronize(ctx->upload_stream);  // whatever was issued no longer reads the slot
     cudaStreamSynchronize(stream);
-    slot->in_flight = false;
+    release_slot(false);
     plan_destroy_impl(plan, false);
     return fail(JS2T_ERR_CUDA, "js2t_batch_fbank: upload: %s", cudaGetErrorString(e));
   }
+  release_slot(true);
   lap("memcpy");
   plan->streams.push_back(stream);  // stream order puts the kernels behind the upload: no ready event
   plan->cmvn_mode = o->cmvn_mode;

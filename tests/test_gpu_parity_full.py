@@ -436,3 +436,61 @@ def test_forked_worker_gets_a_clear_error(fe, fixtures_pcm):
     assert "do not survive fork" in got and "num_workers=0" in got, got
     out, _ = fe.fbank_cmvn_specaug_ragged([fixtures_pcm[0][0]])
     assert np.isfinite(out.cpu().numpy()).all()
+
+
+@pytest.mark.gpu
+def test_threads_with_their_own_streams_get_bit_identical_results(fe):
+    """the reference's functions are called from several loader threads / workers at once, so the
+    CUDA-backed drop-in must be re-entrant per stream.  Four threads, each on its own CUDA stream, push different
+    batches through the one-call entry point (shared context: staging slots, plan pool, upload stream, retired
+    plans) at the same time; every result must equal, bit for bit, what the same call gives single-threaded."""
+    import threading
+
+    import torch
+
+    rng = np.random.RandomState(5)
+    n_threads, n_rounds = 4, 12
+    jobs = []
+    for t in range(n_threads):
+        lens = [int(x) for x in rng.randint(400, 16000 * 6, size=5 + 3 * t)]
+        waves = _mixed_batch(rng, lens)
+        T = np.array([1 + (n - 400) // 160 for n in lens])
+        table = np.zeros((len(waves), 4, 2), np.int32)
+        for u in range(len(waves)):
+            table[u, :2, 0] = rng.randint(0, 60, 2)
+            table[u, :2, 1] = rng.randint(0, 20, 2)
+            table[u, 2:, 0] = rng.randint(0, max(int(T[u]), 1), 2)
+            table[u, 2:, 1] = rng.randint(0, 25, 2)
+        kw = dict(cmvn=dict(norm_means=True, norm_vars=bool(t % 2), before=bool(t < 2)), masks=table, n_fmask=2,
+                  n_tmask=2, layout="padded" if t % 2 else "ragged", pad_value=1.0)
+        jobs.append((waves, kw))
+    expected = []
+    for waves, kw in jobs:
+        out, _ = fe.fbank_cmvn_specaug_ragged(waves, **kw)
+        expected.append(out.cpu().numpy().copy())
+    torch.cuda.synchronize()
+
+    errors, barrier = [], threading.Barrier(n_threads)
+
+    def work(t):
+        try:
+            waves, kw = jobs[t]
+            stream = torch.cuda.Stream()
+            barrier.wait()
+            with torch.cuda.stream(stream):
+                outs = [fe.fbank_cmvn_specaug_ragged(waves, **kw)[0] for _ in range(n_rounds)]
+                stream.synchronize()
+                for o in outs:
+                    got = o.cpu().numpy()
+                    if not np.array_equal(got.view(np.uint32), expected[t].view(np.uint32)):
+                        errors.append(f"thread {t}: result differs from the single-threaded one")
+                        break
+        except Exception as e:  # pylint: disable=broad-except
+            errors.append(f"thread {t}: {e!r}")
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(n_threads)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
