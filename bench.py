@@ -15,6 +15,10 @@ scaling).  A "step" is one pass of the hot path (fbank -> utterance CMVN) over o
 * ``value``     whole-job audio-hours/sec with PCM resident in HBM, CUDA-event timed, max over ranks
 * ``e2e``       same metric through the public host API: pinned host PCM -> H2D -> kernels -> D2H of
                 the features into pinned host memory, every step inside the timed region
+                (``frontend.HostPipeline``: the caller hands over one packed pinned buffer per batch);
+                ``e2e.from_pageable_arrays`` = the same from separate pageable numpy arrays, one per
+                utterance, through the one public per-batch call (gather, upload, kernels, read-back),
+                nothing packed or planned outside the timed region
 * ``roofline``  algorithmic HBM bytes of the dominant kernel / its CUDA-event duration (events are
                 recorded inside the library on the launching stream) against MEASURED_PEAKS.json.
                 The step's three kernels are chained by programmatic dependent launch, which an
