@@ -87,7 +87,7 @@ __device__ __forceinline__ void fft16n(C2 (&v)[NS][16]) {
 constexpr int kSigRow = 32;  // float2 (de, dO) per row and half-warp lane: 18 rows x 16 lanes per frame pair
 
 // ABL (ablation, timing only): 1 = no 16x16 exchange, 2 = no table loads (window / twiddles as constants), 4 = no
-// radix-16 butterflies
+// radix-16 butterflies, 8 = no partner shuffles in the real-input split, 16 = no W512 loads
 template <int NS, int ABL = 0>
 __global__ void __launch_bounds__(256, NS == 1 ? 2 : 1) fft_section_kernel(float* __restrict__ out, int passes) {
   extern __shared__ __align__(16) unsigned char sm[];
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256, NS == 1 ? 2 : 1) fft_section_kernel(float
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = r + 16 * j;
-      const float2 w = (ABL & 2) ? make_float2(0.8f - 0.05f * j, 0.2f + 0.04f * j) : sTw512[k];
+      const float2 w = (ABL & (2 | 16)) ? make_float2(0.8f - 0.05f * j, 0.2f + 0.04f * j) : sTw512[k];
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
         float* Pf = sPw + s * kPFloats + fA;
@@ -210,10 +210,15 @@ __global__ void __launch_bounds__(256, NS == 1 ? 2 : 1) fft_section_kernel(float
         float s0, s1, s2, s3, t0, t1, t2, t3;
         upk(ma.re, s0, s1); upk(ma.im, s2, s3);
         upk(mb.re, t0, t1); upk(mb.im, t2, t3);
-        const float q0 = __shfl_sync(0xffffffffu, r0 ? t0 : s0, partner);
-        const float q1 = __shfl_sync(0xffffffffu, r0 ? t1 : s1, partner);
-        const float q2 = __shfl_sync(0xffffffffu, r0 ? t2 : s2, partner);
-        const float q3 = __shfl_sync(0xffffffffu, r0 ? t3 : s3, partner);
+        float q0, q1, q2, q3;
+        if (ABL & 8) {  // partner values from the lane's own registers: no shuffles, no selects
+          q0 = s0; q1 = s1; q2 = s2; q3 = s3;
+        } else {
+          q0 = __shfl_sync(0xffffffffu, r0 ? t0 : s0, partner);
+          q1 = __shfl_sync(0xffffffffu, r0 ? t1 : s1, partner);
+          q2 = __shfl_sync(0xffffffffu, r0 ? t2 : s2, partner);
+          q3 = __shfl_sync(0xffffffffu, r0 ? t3 : s3, partner);
+        }
         const C2 z = v[s][j];
         const C2 zp = C2{pk(q0, q1), pk(q2, q3)};
         const u64 er = add2(z.re, zp.re), ei = sub2(z.im, zp.im);
@@ -281,6 +286,9 @@ int main() {
   run<1, 4>("NS=1, no butterflies", 2 * sms, 400);
   run<1, 5>("NS=1, no butterflies, no exchange", 2 * sms, 400);
   run<2, 2>("NS=2, no table loads", sms, 400);
+  run<1, 8>("NS=1, no partner shuffles / selects", 2 * sms, 400);
+  run<1, 16>("NS=1, no W512 loads", 2 * sms, 400);
+  run<1, 24>("NS=1, no partner shuffles, no W512 loads", 2 * sms, 400);
   // the product's FFT section for comparison: 61.5 % of 173 us for 318 883 frames = 0.334 ns per frame
   return 0;
 }
