@@ -3,7 +3,7 @@
 set -x
 cd "${GRAFT_REPO_ROOT:-.}"
 nvidia-smi -L | wc -l; nproc
-for n in 8 4; do
+for n in 8; do
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2953$n \
       bench.py --gpus $n --steps 20 --warmup 5 > gpurun_out/r2y_bench_cfg2_n$n.json 2> gpurun_out/r2y_bench_cfg2_n$n.err
   tail -3 gpurun_out/r2y_bench_cfg2_n$n.err
