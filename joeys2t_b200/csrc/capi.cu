@@ -11,6 +11,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <sched.h>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -1216,8 +1218,13 @@ class CopyPool {
 
 CopyPool* copy_pool() {
   static CopyPool* pool = [] {
+    // half of the cores this process may run on, at most 8 threads including the caller (host memory bandwidth is
+    // what limits the gather, and N ranks share the box); JS2T_COPY_THREADS overrides it
     unsigned hw = std::thread::hardware_concurrency();
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) hw = (unsigned)CPU_COUNT(&set);
     int n = hw > 2 ? (int)std::min(hw / 2, 8u) - 1 : 0;  // + the calling thread
+    if (const char* e = getenv("JS2T_COPY_THREADS")) n = std::max(1, std::min(atoi(e), 64)) - 1;
     return new CopyPool(n < 0 ? 0 : n);
   }();
   return pool;
