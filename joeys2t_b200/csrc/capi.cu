@@ -421,6 +421,12 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
     p->pad_tmax = pad_tmax;
   }
   std::vector<TileDesc> tiles;
+  {
+    size_t n_est = 0;
+    for (int u = 0; u < n_utts; ++u)
+      n_est += (size_t)((layout == JS2T_LAYOUT_PADDED ? p->pad_tmax : p->h_utts[u].n_frames) + kTileFrames - 1) / kTileFrames;
+    tiles.reserve(n_est + 1);
+  }
   long long row = 0;
   for (int u = 0; u < n_utts; ++u) {
     UttDesc& d = p->h_utts[u];
@@ -502,8 +508,14 @@ static int plan_create_common(js2t_ctx* ctx, int n_utts, const int64_t* pcm_byte
     tiles.swap(sched);
     p->n_tiles = (int)tiles.size();
   } else {
-    std::stable_sort(tiles.begin(), tiles.end(),
-                     [](const TileDesc& a, const TileDesc& b) { return a.nf > b.nf; });
+    // stable, by valid frames descending: a counting sort over the 33 possible values (a batch of 256 utterances
+    // has ~10 k tiles; a comparison sort was a third of the plan's host time)
+    size_t start[kTileFrames + 2] = {0};
+    for (const TileDesc& t : tiles) ++start[kTileFrames - t.nf + 1];
+    for (int i = 1; i <= kTileFrames + 1; ++i) start[i] += start[i - 1];
+    std::vector<TileDesc> sorted(tiles.size());
+    for (const TileDesc& t : tiles) sorted[start[kTileFrames - t.nf]++] = t;
+    tiles.swap(sorted);
   }
 
   // one device allocation, carved up
